@@ -1,0 +1,146 @@
+/* s2pb200.h -- C ABI of the B200-native stereo engine that drops in behind s2p.
+ *
+ * Plain C, plain pointers and sizes, no torch / numpy types.  The library
+ * (s2p_b200/libs2pb200.so, sources in s2p_b200/csrc/) is loaded with
+ * ctypes.CDLL exactly like the reference loads its own native helpers
+ * (s2p/triangulation.py:18-20, s2p/sift.py:25-26).  INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference):
+ *
+ *   s2pb_mgm()           the `mgm` / `mgm_multi` subprocess + the three
+ *                        plambda/backflow subprocesses of create_rejection_mask
+ *                        (s2p/block_matching.py:18-32,155-188,269-310;
+ *                         3rdparty/mgm_multi/main_mgm.cc:80-266,
+ *                         main_mgm_multi.cc:88-256)
+ *   s2pb_homography()    the `homography` subprocess run by
+ *                        common.image_apply_homography (s2p/common.py:159-180;
+ *                        3rdparty/homography/main.cpp:65-177)
+ *   s2pb_mgm_batch()     the per-(tile,pair) fan-out of stereo_matching through
+ *                        parallel.launch_calls (s2p/__init__.py:166-196,586-591)
+ *
+ * Conventions: all images are single-band, row-major, C-contiguous float32,
+ * NaN = no data.  Disparity d at ref pixel (x,y) means the match is at
+ * (x+d, y) in the secondary image.  Every function returns S2PB_OK (0) or a
+ * negative error code; s2pb_last_error() gives the message (thread local).
+ * There is no CPU fallback: without a CUDA device every compute call fails with
+ * S2PB_ERR_CUDA.
+ */
+#ifndef S2PB200_H
+#define S2PB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2PB_VERSION 100
+
+enum {
+    S2PB_OK = 0,
+    S2PB_ERR_CUDA = -1,      /* CUDA runtime / kernel failure, or no device          */
+    S2PB_ERR_ARG = -2,       /* invalid argument (the reference would exit non-zero)  */
+    S2PB_ERR_TIMEOUT = -3,   /* params.timeout_ms exceeded -> subprocess.TimeoutExpired */
+    S2PB_ERR_NOMEM = -4,     /* tile does not fit the device workspace                */
+    S2PB_ERR_UNSUPPORTED = -5
+};
+
+/* Matcher parameters.  In the reference these travel as argv + environment
+ * "smart parameters" (3rdparty/mgm_multi/smartparameter.h:27-51); the comment
+ * on each field names the flag it mirrors. */
+typedef struct s2pb_mgm_params {
+    int32_t ndir;            /* -O           number of scan passes: 2, 4 or 8            */
+    int32_t tsgm;            /* TSGM         neighbours mixed per pass: 1..4             */
+    int32_t census_win;      /* CENSUS_NCC_WIN  census window side: 3, 5 or 7            */
+    float   P1;              /* -P1                                                       */
+    float   P2;              /* -P2                                                       */
+    int32_t median;          /* MEDIAN       radius of the median post-filter, 0 = off    */
+    int32_t lr_mode;         /* TESTLRRL     0 off, 1 per scale, 2 once at the end        */
+    float   lr_tau;          /* TESTLRRL_TAU                                              */
+    float   mindiff;         /* MINDIFF      < 0 = off                                    */
+    int32_t remove_small_cc; /* REMOVESMALLCC  0 = off                                    */
+    int32_t subpix;          /* SUBPIX       1, or 2 for the half-pixel pass (mgm_multi)  */
+    int32_t scales;          /* -S           < 0: single-scale `mgm`; >= 0: `mgm_multi`   */
+    int32_t refine;          /* -s           0 none, 1 vfit, 2 parabola                   */
+    int32_t fix_overcount;   /* TSGM_FIX_OVERCOUNT                                        */
+    int32_t timeout_ms;      /* <= 0: none.  mirrors common.run(timeout=) for mgm*        */
+} s2pb_mgm_params;
+
+typedef struct s2pb_ctx s2pb_ctx;   /* one per (process, GPU); not thread safe */
+
+/* ---- library / context ---------------------------------------------------- */
+int          s2pb_version(void);
+const char  *s2pb_last_error(void);
+int          s2pb_device_count(void);               /* 0 if no usable CUDA device */
+/* CUDA is initialised here, never at load time, so a forked multiprocessing
+ * worker (s2p/parallel.py:80) can create its context after the fork. */
+s2pb_ctx    *s2pb_create(int device);
+void         s2pb_destroy(s2pb_ctx *ctx);
+/* algo = "mgm" or "mgm_multi": the values s2p sets at s2p/block_matching.py:155-186,269-308 */
+int          s2pb_default_params(const char *algo, s2pb_mgm_params *p);
+
+/* ---- the matcher ----------------------------------------------------------- */
+/* Host buffers in, host buffers out (H2D/D2H inside).  disp, conf: w*h float32;
+ * mask: w*h uint8 (0 rejected / 1 accepted) or NULL; disp_right: w*h or NULL. */
+int s2pb_mgm(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h,
+             int dmin, int dmax, const s2pb_mgm_params *p,
+             float *disp, float *conf, uint8_t *mask, float *disp_right);
+
+/* Same, device pointers on both sides, enqueued on `stream` (a cudaStream_t
+ * passed as void*, NULL = the context's own stream) and NOT synchronised when
+ * timeout_ms <= 0.  `slot` selects one of the context's workspaces
+ * (0 <= slot < s2pb_num_slots) so that several tiles can be in flight. */
+int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, const float *d_im2,
+                    int w, int h, int dmin, int dmax, const s2pb_mgm_params *p,
+                    float *d_disp, float *d_conf, uint8_t *d_mask, float *d_disp_right,
+                    void *stream);
+
+/* n independent tiles of identical shape, pipelined over the context's slots
+ * (pinned staging + H2D, compute, D2H overlap).  Arrays of n host pointers. */
+int s2pb_mgm_batch(s2pb_ctx *ctx, int n, const float *const *im1, const float *const *im2,
+                   int w, int h, int dmin, int dmax, const s2pb_mgm_params *p,
+                   float *const *disp, float *const *conf, uint8_t *const *mask);
+
+/* Reserve `nslots` workspaces for tiles up to w x h x (dmax-dmin+1) labels.
+ * Optional: s2pb_mgm* grow the workspace on demand. */
+int s2pb_reserve(s2pb_ctx *ctx, int nslots, int w, int h, int nlabels);
+int s2pb_num_slots(const s2pb_ctx *ctx);
+int s2pb_sync(s2pb_ctx *ctx);
+
+/* ---- rectification warp ---------------------------------------------------- */
+/* dst(j,i) = src sampled at H^-1 (j,i,1), order-5 B-spline with the reference's
+ * anti-aliasing rule (3rdparty/homography/LibHomography/Homography.cpp:50-168). */
+int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh,
+                    const double H[9], float *dst, int dw, int dh);
+
+/* ---- stage-level entry points (host buffers; used by the parity tests) ----- */
+/* census_tools.cc:127-153.  codes: w*h uint64, first neighbour in the top bit. */
+int s2pb_census(s2pb_ctx *ctx, const float *img, int w, int h, int win, uint64_t *codes);
+/* mgm_costvolume.cc:74-174.  lo/hi: per-pixel label range (int32, inclusive);
+ * C: w*h*D float32, slot k <-> label gmin+k, +INF outside the range / image. */
+int s2pb_costvolume(s2pb_ctx *ctx, const float *u, const float *v, int w, int h,
+                    const int32_t *lo, const int32_t *hi, int gmin, int D, int win, float *C);
+/* mgm_core.cc:829-1074 on a caller-supplied volume.  S (nullable): w*h*D. */
+int s2pb_aggregate(s2pb_ctx *ctx, const float *C, const int32_t *lo, const int32_t *hi,
+                   int w, int h, int gmin, int D, float P1, float P2, int ndir, int tsgm,
+                   int fix_overcount, float *S, float *disp, float *cost, float *conf);
+/* img_tools.h:204-238 */
+int s2pb_median(s2pb_ctx *ctx, const float *in, float *out, int w, int h, int radius);
+/* s2p/block_matching.py:18-32 (plambda + backflow + plambda) */
+int s2pb_rejection_mask(s2pb_ctx *ctx, const float *disp, const float *im1, const float *im2,
+                        int w, int h, uint8_t *mask);
+
+/* ---- instrumentation -------------------------------------------------------- */
+enum { S2PB_T_CENSUS = 0, S2PB_T_COST, S2PB_T_AGGREGATE, S2PB_T_WTA, S2PB_T_POST, S2PB_T_TOTAL, S2PB_T_COUNT };
+/* CUDA-event milliseconds of the stages of the last s2pb_mgm / s2pb_mgm_device
+ * call on `slot` (valid after the stream has been synchronised). */
+int s2pb_last_timings(s2pb_ctx *ctx, int slot, float ms[S2PB_T_COUNT]);
+/* number of kernels this library has launched since the context was created */
+long long s2pb_kernel_launches(const s2pb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2PB200_H */

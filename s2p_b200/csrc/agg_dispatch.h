@@ -1,0 +1,12 @@
+// agg_dispatch.h -- host-side dispatch to the per-LPL instantiations of aggregate_kernel.
+// Each agg_inst.cu object (compiled with -DS2PB_LPL=n) carries the four TSGM variants for one
+// labels-per-lane value, so the instantiations build in parallel.
+#pragma once
+#include "agg_kernel.cuh"
+
+namespace s2pb {
+template <int LPL> int agg_launch_lpl(int tsgm, const AggParams &P, int sm_count, cudaStream_t st);
+template <int LPL> int agg_configure_lpl();
+int agg_configure();                                   // 0 ok
+int agg_launch(int LPL, int tsgm, const AggParams &P, int sm_count, cudaStream_t st);   // 0 ok, -1 CUDA error, -2 unsupported
+}  // namespace s2pb

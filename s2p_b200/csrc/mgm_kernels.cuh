@@ -1,0 +1,302 @@
+// mgm_kernels.cuh -- census, cost volume, WTA / sub-pixel and image-space post-filter kernels.
+// Layout, reference citations and numerical conventions: see the header of agg_kernel.cuh.
+#pragma once
+#include "agg_kernel.cuh"
+
+namespace s2pb {
+
+// ------------------------------------------------------------------ census
+
+// census_tools.cc:38-57: neighbours in row-major window order, centre skipped,
+// bit = (centre < neighbour), out-of-image neighbour compares as NaN -> 0.
+__global__ void census_kernel(const float *__restrict__ img, int w, int h, int r, uint64_t *__restrict__ codes)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float c = img[(size_t)y * w + x];
+    uint64_t code = 0;
+    for (int j = -r; j <= r; j++)
+        for (int i = -r; i <= r; i++) {
+            if (i == 0 && j == 0) continue;
+            int xx = x + i, yy = y + j;
+            unsigned bit = 0;
+            if (xx >= 0 && xx < w && yy >= 0 && yy < h) bit = c < img[(size_t)yy * w + xx];
+            code = (code << 1) | bit;
+        }
+    codes[(size_t)y * w + x] = code;
+}
+
+// main_mgm.cc:172-173,178,207,210-216: NaN -> 0 and the per-pixel label range of one view.
+// `sentinel` is the reference's dmin (sic, for BOTH views) used for no-data pixels.
+__global__ void prepare_view_kernel(const float *__restrict__ in, int n, int lo_all, int hi_all, int sentinel,
+                                    float *__restrict__ clean, short *__restrict__ lo, short *__restrict__ hi)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = in[i];
+    bool isn = isnan(v);
+    clean[i] = isfinite(v) ? v : 0.f;
+    lo[i] = (short)(isn ? sentinel : lo_all);
+    hi[i] = (short)(isn ? sentinel + 1 : hi_all);
+}
+
+// ------------------------------------------------------------------ cost volume
+
+// One warp per pixel.  mgm_costvolume.cc:140-172: label o of pixel (x,y) compares census
+// codes cu(x,y) and cv(x+o,y); +INF when x+o is outside; if no label of the pixel's range is
+// finite, the whole range is set to 0.  Slots outside [lo,hi] stay +INF.
+template <int LPL>
+__global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__restrict__ cv, int w, int h,
+                            const short *__restrict__ lo, const short *__restrict__ hi, int gmin, __half *__restrict__ C)
+{
+    constexpr int DP = 32 * LPL;
+    int lane = threadIdx.x & 31;
+    size_t npix = (size_t)w * h;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < npix; p += nwarps) {
+        int x = (int)(p % w);
+        size_t row = p - x;
+        uint64_t a = cu[p];
+        int l = lo[p], hgh = hi[p];
+        float c[LPL];
+        bool anyfinite = false;
+#pragma unroll
+        for (int e = 0; e < LPL; e++) {
+            int o = gmin + lane * LPL + e;
+            float v = S2PB_INF;
+            if (o >= l && o <= hgh) {
+                int q = x + o;
+                if (q >= 0 && q < w) { v = (float)__popcll(a ^ cv[row + q]); anyfinite = true; }
+            }
+            c[e] = v;
+        }
+        if (!__any_sync(0xffffffffu, anyfinite)) {
+#pragma unroll
+            for (int e = 0; e < LPL; e++) {
+                int o = gmin + lane * LPL + e;
+                if (o >= l && o <= hgh) c[e] = 0.f;
+            }
+        }
+        __half *dst = C + p * DP + lane * LPL;
+#pragma unroll
+        for (int e = 0; e < LPL; e++) dst[e] = __float2half_rn(c[e]);
+    }
+}
+
+// float volume (stage-level API) -> f16 slab with +INF padding, and back
+__global__ void pack_cost_kernel(const float *__restrict__ Cin, size_t npix, int D, int DP, __half *__restrict__ C)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix * DP) return;
+    size_t p = i / DP; int k = (int)(i % DP);
+    C[i] = __float2half_rn(k < D ? Cin[p * D + k] : S2PB_INF);
+}
+__global__ void unpack_cost_kernel(const __half *__restrict__ C, size_t npix, int D, int DP, const float *__restrict__ lut,
+                                   float *__restrict__ Cout)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix * D) return;
+    size_t p = i / D; int k = (int)(i % D);
+    Cout[i] = cost_value(__half_as_ushort(C[p * DP + k]), lut);
+}
+
+// ------------------------------------------------------------------ WTA + consensus + sub-pixel
+
+struct WtaParams {
+    const float *L[kMaxPasses];
+    const short *arg[kMaxPasses];
+    const __half *C;
+    const short *lo, *hi;     // per-pixel label range (labels, not slots)
+    const float *lut;
+    int ndir, gmin, fix_overcount, refine;
+    float inv_zoom_div;       // ZOOMFACTOR (disparity is divided by it, mgm_multiscale.cc:253)
+    size_t npix;
+    float *S;                 // optional [npix][D] dense output (stage API / PKR), D = Dout
+    int Dout;
+    float *disp, *cost, *conf;
+};
+
+__device__ __forceinline__ void vfit3(float v0, float v1, float v2, float &vmin, float &xmin)
+{   // refine.h:70-92
+    if ((v1 > v0) && (v1 > v2)) { vmin = v1; xmin = 0.f; return; }
+    float slope = v2 - v1;
+    if ((v2 - v1) < (v0 - v1)) slope = v0 - v1;
+    xmin = __fdiv_rn(v0 - v2, 2.f * slope);
+    vmin = v2 + (xmin - 1.f) * slope;
+}
+__device__ __forceinline__ void parabola3(float v0, float v1, float v2, float &vmin, float &xmin)
+{   // refine.h:40-68
+    if (v1 > v0 && v1 > v2) { xmin = 0.f; vmin = v1; return; }
+    float c = v1;
+    float b = __fdiv_rn(v2 - v0, 2.f);
+    float a = __fdiv_rn(v2 - 2.f * v1 + v0, 2.f);
+    float x = __fdiv_rn(-b, 2.f * a);
+    if (x > 1.f) x = 1.f;
+    if (x < -1.f) x = -1.f;
+    vmin = (a * x + b) * x + c;
+    xmin = x;
+}
+
+// One warp per pixel: S = (L0+L1+...+L_{ndir-1}) - (ndir-1) C in pass order (dvec.cc:110-118,
+// mgm_core.cc:1041-1042), first strict minimum over finite S (:1044-1048), consensus (:1054-1057),
+// V-fit / parabola on S[o-1..o+1] when o-1 >= lo and o+2 <= hi (mgm_refine.h:67-84).
+template <int LPL>
+__global__ void wta_kernel(const WtaParams P)
+{
+    constexpr int DP = 32 * LPL;
+    __shared__ float sS[8][DP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < P.npix; p += nwarps) {
+        float s[LPL];
+#pragma unroll
+        for (int e = 0; e < LPL; e++) s[e] = 0.f;
+        for (int d = 0; d < P.ndir; d++) {
+            float v[LPL];
+            ld_vec_cg<LPL>(P.L[d] + p * DP + lane * LPL, v);
+#pragma unroll
+            for (int e = 0; e < LPL; e++) s[e] += v[e];
+        }
+        HalfPack<LPL> cp = ld_cost<LPL>(P.C + p * DP + lane * LPL);
+        float best = S2PB_INF;
+        int bidx = 0x7fffffff;
+#pragma unroll
+        for (int e = 0; e < LPL; e++) {
+            float c = cost_value(cp.h[e], P.lut);
+            if (P.fix_overcount == 1) s[e] = fmaf(-(float)(P.ndir - 1), c, s[e]);
+            if (isfinite(s[e]) && best > s[e]) { best = s[e]; bidx = lane * LPL + e; }
+        }
+        const float m = warp_min_f32(best);
+        int cand = (best == m && bidx != 0x7fffffff) ? bidx : 0x7fffffff;
+        const int kbest = __reduce_min_sync(0xffffffffu, cand);   // first slot attaining the minimum
+        // every pixel has at least one finite S (its range always holds a finite cost)
+        const int o = P.gmin + kbest;
+        float minP = (float)o, minL = m;
+
+        int confi = 0;
+        if (lane < P.ndir) confi = (P.arg[lane][p] == kbest) ? 1 : 0;
+        confi = __reduce_add_sync(0xffffffffu, confi);
+
+        if (P.S != nullptr || P.refine != 0) {
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < LPL; e++) sS[wib][lane * LPL + e] = s[e];
+            __syncwarp();
+        }
+        if (P.S != nullptr) {
+            const int lo = P.lo[p] - P.gmin, hi = P.hi[p] - P.gmin;
+            for (int kk = lane; kk < P.Dout; kk += 32)
+                P.S[p * P.Dout + kk] = (kk >= lo && kk <= hi) ? sS[wib][kk] : S2PB_INF;
+        }
+        if (P.refine != 0 && lane == 0) {
+            if (o - 1 >= P.lo[p] && o + 2 <= P.hi[p]) {
+                const float v0 = sS[wib][kbest - 1], v1 = sS[wib][kbest], v2 = sS[wib][kbest + 1];
+                float dx = 0.f, dxr = 0.f, ml = minL, mlr = minP;
+                if (P.refine == 1) { vfit3(v0, v1, v2, ml, dx); vfit3(v2, v1, v0, mlr, dxr); }
+                else { parabola3(v0, v1, v2, ml, dx); parabola3(v2, v1, v0, mlr, dxr); }
+                minP = (float)o + dx;
+                minL = ml;
+                if (mlr < ml) { minP = (float)o - dxr; minL = mlr; }
+            }
+        }
+        if (lane == 0) {
+            P.disp[p] = __fdiv_rn(minP, P.inv_zoom_div);
+            if (P.cost) P.cost[p] = minL;
+            if (P.conf) P.conf[p] = (float)confi;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ image-space post filters
+
+// median_filter, img_tools.h:204-238: window clipped to the image, NaN skipped, element
+// size/2 of the sorted values; pixel unchanged when the window holds no value.
+__global__ void median_kernel(const float *__restrict__ in, float *__restrict__ out, int w, int h, int radius)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float v[25];
+    int n = 0;
+    for (int j = -radius; j <= radius; j++) {
+        int yy = y + j;
+        if (yy < 0 || yy >= h) continue;
+        for (int i = -radius; i <= radius; i++) {
+            int xx = x + i;
+            if (xx < 0 || xx >= w) continue;
+            float t = in[(size_t)yy * w + xx];
+            if (!isnan(t)) {   // insertion sort
+                int q = n++;
+                while (q > 0 && v[q - 1] > t) { v[q] = v[q - 1]; q--; }
+                v[q] = t;
+            }
+        }
+    }
+    out[(size_t)y * w + x] = n ? v[n / 2] : in[(size_t)y * w + x];
+}
+
+// leftright_test, stereo_utils.cc:9-32: `out` = `dx` with the pixels failing the test set to NaN;
+// `other` is the other view's disparity BEFORE its own test (mgm_multiscale.cc:322-327).
+__global__ void lrcheck_kernel(const float *__restrict__ dx, const float *__restrict__ other, float *__restrict__ out,
+                               int w, int h, float tau)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    size_t i = (size_t)y * w + x;
+    float d = dx[i], r = d;
+    float t = (float)x + d;
+    if (!isfinite(t)) r = __int_as_float(0x7fc00000);
+    else {
+        float rt = roundf(t);
+        if (rt < (float)w && rt >= 0.f) {
+            int Lx = (int)rt;
+            float Rx = (float)Lx + other[(size_t)y * w + Lx];
+            if (fabs((double)(Rx - (float)x)) > (double)tau) r = __int_as_float(0x7fc00000);
+        } else r = __int_as_float(0x7fc00000);
+    }
+    out[i] = r;
+}
+
+// main_mgm.cc:231-236 : no-data pixels of the view's own image get NaN
+__global__ void nan_restore_kernel(float *__restrict__ d, const float *__restrict__ orig, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && isnan(orig[i])) d[i] = __int_as_float(0x7fc00000);
+}
+
+__device__ __forceinline__ float cubic1(const float v[4], float x)
+{   // c/bicubic.c:8-13 -- double arithmetic through the literals, result narrowed to float
+    double xd = x;
+    return (float)((double)v[1] + 0.5 * xd * ((double)v[2] - (double)v[0]
+                   + xd * (2.0 * v[0] - 5.0 * v[1] + 4.0 * v[2] - (double)v[3]
+                   + xd * (3.0 * ((double)v[1] - (double)v[2]) + (double)v[3] - (double)v[0]))));
+}
+// create_rejection_mask (s2p/block_matching.py:18-32): backflow samples im2 at (x+d, y) with the
+// zero-boundary bicubic of c/bicubic.c:69-96, mask = finite(disp) & finite(im1) & finite(sample).
+__global__ void rejection_mask_kernel(const float *__restrict__ disp, const float *__restrict__ im1,
+                                      const float *__restrict__ im2, int w, int h, uint8_t *__restrict__ mask)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= w || j >= h) return;
+    size_t idx = (size_t)j * w + i;
+    float d = disp[idx];
+    float x = ((float)i + d) - 1.f, y = (float)j - 1.f;
+    float r;
+    if (!isfinite(x)) r = x;
+    else {
+        int ix = (int)floorf(x), iy = (int)floorf(y);
+        float vv[4];
+        for (int ii = 0; ii < 4; ii++) {
+            float col[4];
+            for (int jj = 0; jj < 4; jj++) {
+                int sx = ix + ii, sy = iy + jj;
+                col[jj] = (sx < 0 || sx >= w || sy < 0 || sy >= h) ? 0.f : im2[(size_t)sy * w + sx];
+            }
+            vv[ii] = cubic1(col, y - (float)iy);
+        }
+        r = cubic1(vv, x - (float)ix);
+    }
+    mask[idx] = (isfinite(d) && isfinite(im1[idx]) && isfinite(r)) ? 1 : 0;
+}
+
+}  // namespace s2pb

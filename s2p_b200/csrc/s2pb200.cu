@@ -1,0 +1,815 @@
+// s2pb200.cu -- context, workspace and the C ABI declared in include/s2pb200.h.
+//
+// Host-side orchestration of the kernels in mgm_kernels.cuh.  The sequence of stages mirrors
+// what one `mgm` process does for one tile (main_mgm.cc:167-262 -> mgm_call,
+// mgm_multiscale.cc:161-335 in the reference) followed by create_rejection_mask
+// (s2p/block_matching.py:18-32).  There is no CPU fallback in this file.
+#include "../../include/s2pb200.h"
+#include "mgm_kernels.cuh"
+#include "agg_dispatch.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace s2pb;
+
+// ------------------------------------------------------------------ errors
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(S2PB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------ context
+
+struct ViewWS {
+    float *img;            // NaN-free copy
+    short *lo, *hi;        // per-pixel label range
+    uint64_t *census;
+    __half *C;
+    float *L[kMaxPasses];
+    float *Lmin[kMaxPasses];
+    short *arg[kMaxPasses];
+    int *progress;         // [kMaxPasses][maxBands]
+    float *disp, *cost, *conf, *tmp;
+};
+struct Slot {
+    void *base = nullptr;
+    size_t bytes = 0;
+    int w = 0, h = 0, DP = 0, ndir = 0;
+    ViewWS v[2];
+    int *next_item = nullptr;
+    float *lut = nullptr;
+    // staging for the host-buffer API
+    float *d_in[2] = {nullptr, nullptr};
+    float *d_disp = nullptr, *d_conf = nullptr, *d_dispR = nullptr;
+    uint8_t *d_mask = nullptr;
+    float *h_in[2] = {nullptr, nullptr};          // pinned
+    float *h_disp = nullptr, *h_conf = nullptr, *h_dispR = nullptr;
+    uint8_t *h_mask = nullptr;
+    size_t h_pix = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[S2PB_T_COUNT + 1] = {};
+    cudaEvent_t done = nullptr;
+    bool timed = false;
+};
+struct s2pb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    std::vector<Slot> slots;
+    int *abort_flag = nullptr;     // pinned + mapped: the host raises it on timeout
+    long long launches = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int lpl_for(int D)
+{
+    static const int opts[] = {1, 2, 3, 4, 5, 6, 8, 12, 16};
+    for (int o : opts) if (32 * o >= D) return o;
+    return -1;
+}
+static int max_bands(int w, int h) { return ((w > h ? w : h) + kNW - 1) / kNW; }
+
+static int slot_layout(Slot &s, int w, int h, int DP, int ndir, bool allocate)
+{
+    // carve one allocation; called first with allocate=false to size it
+    size_t npix = (size_t)w * h, off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    char *b = (char *)s.base;
+    int mb = max_bands(w, h);
+    for (int vi = 0; vi < 2; vi++) {
+        ViewWS &v = s.v[vi];
+        size_t o;
+        o = take(npix * 4); if (allocate) v.img = (float *)(b + o);
+        o = take(npix * 2); if (allocate) v.lo = (short *)(b + o);
+        o = take(npix * 2); if (allocate) v.hi = (short *)(b + o);
+        o = take(npix * 8); if (allocate) v.census = (uint64_t *)(b + o);
+        o = take(npix * DP * 2); if (allocate) v.C = (__half *)(b + o);
+        for (int p = 0; p < ndir; p++) {
+            o = take(npix * DP * 4); if (allocate) v.L[p] = (float *)(b + o);
+            o = take(npix * 4); if (allocate) v.Lmin[p] = (float *)(b + o);
+            o = take(npix * 2); if (allocate) v.arg[p] = (short *)(b + o);
+        }
+        o = take((size_t)kMaxPasses * mb * 4); if (allocate) v.progress = (int *)(b + o);
+        o = take(npix * 4); if (allocate) v.disp = (float *)(b + o);
+        o = take(npix * 4); if (allocate) v.cost = (float *)(b + o);
+        o = take(npix * 4); if (allocate) v.conf = (float *)(b + o);
+        o = take(npix * 4); if (allocate) v.tmp = (float *)(b + o);
+    }
+    size_t o;
+    o = take(256); if (allocate) s.next_item = (int *)(b + o);
+    o = take(256); if (allocate) s.lut = (float *)(b + o);
+    for (int i = 0; i < 2; i++) { o = take(npix * 4); if (allocate) s.d_in[i] = (float *)(b + o); }
+    o = take(npix * 4); if (allocate) s.d_disp = (float *)(b + o);
+    o = take(npix * 4); if (allocate) s.d_conf = (float *)(b + o);
+    o = take(npix * 4); if (allocate) s.d_dispR = (float *)(b + o);
+    o = take(npix); if (allocate) s.d_mask = (uint8_t *)(b + o);
+    if (!allocate) s.bytes = off;
+    return 0;
+}
+
+static int slot_ensure(s2pb_ctx *ctx, Slot &s, int w, int h, int DP, int ndir)
+{
+    if (s.base && s.w == w && s.h == h && s.DP == DP && s.ndir >= ndir) return S2PB_OK;
+    Slot probe;
+    slot_layout(probe, w, h, DP, ndir, false);
+    if (!s.base || probe.bytes > s.bytes) {
+        if (s.base) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.base)); s.base = nullptr; }
+        cudaError_t e = cudaMalloc(&s.base, probe.bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            s.base = nullptr; s.bytes = 0;
+            return fail(S2PB_ERR_NOMEM, "workspace of %.2f GiB for a %dx%dx%d tile does not fit: %s",
+                        probe.bytes / 1073741824.0, w, h, DP, cudaGetErrorString(e));
+        }
+        s.bytes = probe.bytes;
+    } else {
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    s.w = w; s.h = h; s.DP = DP; s.ndir = ndir;
+    size_t keep = s.bytes;
+    slot_layout(s, w, h, DP, ndir, true);
+    s.bytes = keep;
+    return S2PB_OK;
+}
+
+static int slot_host_ensure(Slot &s, size_t npix)
+{
+    if (s.h_pix >= npix) return S2PB_OK;
+    if (s.h_in[0]) { cudaFreeHost(s.h_in[0]); s.h_in[0] = nullptr; }
+    // one pinned block: 2 inputs, disp, conf, dispR (float) + mask (u8)
+    char *p = nullptr;
+    CK(cudaMallocHost((void **)&p, npix * (5 * 4 + 1) + 1024));
+    s.h_in[0] = (float *)p;
+    s.h_in[1] = s.h_in[0] + npix;
+    s.h_disp = s.h_in[1] + npix;
+    s.h_conf = s.h_disp + npix;
+    s.h_dispR = s.h_conf + npix;
+    s.h_mask = (uint8_t *)(s.h_dispR + npix);
+    s.h_pix = npix;
+    return S2PB_OK;
+}
+
+static int slot_init(s2pb_ctx *ctx, Slot &s)
+{
+    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (auto &e : s.ev) CK(cudaEventCreate(&e));
+    CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    return S2PB_OK;
+}
+
+// ------------------------------------------------------------------ library / context entry points
+
+extern "C" int s2pb_version(void) { return S2PB_VERSION; }
+extern "C" const char *s2pb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int s2pb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" s2pb_ctx *s2pb_create(int device)
+{
+    int n = s2pb_device_count();
+    if (n <= 0) { fail(S2PB_ERR_CUDA, "no CUDA device is visible: this library has no CPU path"); return nullptr; }
+    if (device < 0 || device >= n) { fail(S2PB_ERR_ARG, "device %d out of range [0,%d)", device, n); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(S2PB_ERR_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail(S2PB_ERR_CUDA, "cudaGetDeviceProperties failed"); return nullptr; }
+    if (prop.major != 10) {
+        fail(S2PB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    s2pb_ctx *ctx = new s2pb_ctx;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaHostAlloc((void **)&ctx->abort_flag, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+        fail(S2PB_ERR_CUDA, "cudaHostAlloc failed"); delete ctx; return nullptr;
+    }
+    *ctx->abort_flag = 0;
+    ctx->slots.resize(1);
+    if (slot_init(ctx, ctx->slots[0]) != S2PB_OK) { delete ctx; return nullptr; }
+    if (agg_configure() != 0) { fail(S2PB_ERR_CUDA, "cudaFuncSetAttribute failed for the aggregation kernels"); delete ctx; return nullptr; }
+    return ctx;
+}
+
+extern "C" void s2pb_destroy(s2pb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto &s : ctx->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.base) cudaFree(s.base);
+        if (s.h_in[0]) cudaFreeHost(s.h_in[0]);
+        for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (ctx->abort_flag) cudaFreeHost(ctx->abort_flag);
+    delete ctx;
+}
+
+extern "C" int s2pb_default_params(const char *algo, s2pb_mgm_params *p)
+{
+    if (!algo || !p) return fail(S2PB_ERR_ARG, "null argument");
+    memset(p, 0, sizeof *p);
+    p->ndir = 8; p->census_win = 5; p->P1 = 8.f; p->P2 = 32.f; p->lr_mode = 1; p->lr_tau = 1.f;
+    p->mindiff = -1.f; p->refine = 1; p->fix_overcount = 1; p->timeout_ms = 0;
+    if (!strcmp(algo, "mgm")) {          // s2p/block_matching.py:155-186
+        p->tsgm = 3; p->median = 1; p->remove_small_cc = 0; p->subpix = 1; p->scales = -1;
+    } else if (!strcmp(algo, "mgm_multi")) {   // s2p/block_matching.py:269-308 ; TSGM default 4 (mgm_multiscale.cc:120)
+        p->tsgm = 4; p->median = 0; p->remove_small_cc = 25; p->subpix = 2; p->scales = 6;
+    } else return fail(S2PB_ERR_ARG, "unknown algo '%s'", algo);
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_num_slots(const s2pb_ctx *ctx) { return ctx ? (int)ctx->slots.size() : 0; }
+extern "C" long long s2pb_kernel_launches(const s2pb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int s2pb_sync(s2pb_ctx *ctx)
+{
+    if (!ctx) return fail(S2PB_ERR_ARG, "null context");
+    CK(cudaSetDevice(ctx->device));
+    for (auto &s : ctx->slots) if (s.stream) CK(cudaStreamSynchronize(s.stream));
+    return S2PB_OK;
+}
+
+static int ensure_slots(s2pb_ctx *ctx, int nslots)
+{
+    while ((int)ctx->slots.size() < nslots) {
+        ctx->slots.emplace_back();
+        int r = slot_init(ctx, ctx->slots.back());
+        if (r != S2PB_OK) return r;
+    }
+    return S2PB_OK;
+}
+
+// ------------------------------------------------------------------ stage launchers
+
+static dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
+
+static int check_params(const s2pb_mgm_params *p, int w, int h, int dmin, int dmax)
+{
+    if (!p) return fail(S2PB_ERR_ARG, "null params");
+    if (w < 2 || h < 2) return fail(S2PB_ERR_ARG, "image too small (%dx%d)", w, h);
+    if (dmax <= dmin) return fail(S2PB_ERR_ARG, "need dmin < dmax (got %d, %d)", dmin, dmax);
+    if (p->ndir != 2 && p->ndir != 4 && p->ndir != 8) return fail(S2PB_ERR_ARG, "ndir must be 2, 4 or 8");
+    if (p->tsgm < 1 || p->tsgm > 4) return fail(S2PB_ERR_ARG, "tsgm must be 1..4");
+    if (p->census_win != 3 && p->census_win != 5 && p->census_win != 7) return fail(S2PB_ERR_ARG, "census_win must be 3, 5 or 7");
+    if (p->median < 0 || p->median > 2) return fail(S2PB_ERR_ARG, "median radius must be 0..2");
+    if (p->refine < 0 || p->refine > 2) return fail(S2PB_ERR_ARG, "refine must be 0 (none), 1 (vfit) or 2 (parabola)");
+    if (p->scales >= 0 || p->subpix > 1)
+        return fail(S2PB_ERR_UNSUPPORTED, "mgm_multi (multiscale / SUBPIX=2) is not implemented in this build");
+    if (p->remove_small_cc > 0) return fail(S2PB_ERR_UNSUPPORTED, "REMOVESMALLCC is not implemented in this build");
+    if (p->mindiff >= 0) return fail(S2PB_ERR_UNSUPPORTED, "MINDIFF is not implemented in this build");
+    if (p->lr_mode != 0 && p->lr_mode != 1) return fail(S2PB_ERR_UNSUPPORTED, "TESTLRRL=2 only exists in mgm_multi");
+    if (abs(dmin) > 16000 || abs(dmax) > 16000) return fail(S2PB_ERR_ARG, "disparity bounds out of the int16 label range");
+    return S2PB_OK;
+}
+
+// cost LUT for scaled census costs: cost(r) = (float)((double)r * ratio / nch), mgm_costvolume.h:90-91
+static bool cost_lut(int win, float lut[64])
+{
+    int nbits = win * win - 1, nch = (nbits / 8 + 3) / 4;
+    const float ratio = (float)(5 * 5 / ((double)win * win));
+    bool identity = true;
+    for (int r = 0; r < 64; r++) {
+        float fr = (float)r;
+        lut[r] = (float)((double)fr * 1.0 * (double)ratio / nch);
+        if (lut[r] != fr) identity = false;
+    }
+    return !identity;
+}
+
+struct ViewJob {
+    int gmin, D;
+};
+
+static void fill_pass(PassDesc &pd, int pass, int w, int h)
+{
+    const long long W = w, H = h;
+    switch (pass) {   // scan coordinates of the table at mgm_core.cc:884-891
+    case 0: pd.nS = h; pd.nI = w; pd.base = 0;                     pd.strideS = w;  pd.strideI = 1;  pd.type = 0; break;
+    case 1: pd.nS = h; pd.nI = w; pd.base = (H - 1) * W + (W - 1); pd.strideS = -w; pd.strideI = -1; pd.type = 0; break;
+    case 2: pd.nS = w; pd.nI = h; pd.base = (H - 1) * W;           pd.strideS = 1;  pd.strideI = -w; pd.type = 0; break;
+    case 3: pd.nS = w; pd.nI = h; pd.base = W - 1;                 pd.strideS = -1; pd.strideI = w;  pd.type = 0; break;
+    case 4: pd.nS = h; pd.nI = w; pd.base = W - 1;                 pd.strideS = w;  pd.strideI = -1; pd.type = 1; break;
+    case 5: pd.nS = w; pd.nI = h; pd.base = (H - 1) * W + (W - 1); pd.strideS = -1; pd.strideI = -w; pd.type = 1; break;
+    case 6: pd.nS = h; pd.nI = w; pd.base = (H - 1) * W;           pd.strideS = -w; pd.strideI = 1;  pd.type = 1; break;
+    default: pd.nS = w; pd.nI = h; pd.base = 0;                    pd.strideS = 1;  pd.strideI = w;  pd.type = 1; break;
+    }
+    pd.nBands = (pd.nS + kNW - 1) / kNW;
+}
+
+// Enqueue the 8-pass aggregation of `nviews` views of slot s in ONE persistent launch.
+static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, int LPL, float P1, float P2, int ndir, int tsgm,
+                            const float *lut, cudaStream_t st)
+{
+    AggParams P;
+    memset(&P, 0, sizeof P);
+    int mb = max_bands(w, h);
+    P.nPV = 0; P.maxBands = 0;
+    for (int vi = 0; vi < nviews; vi++) {
+        CK(cudaMemsetAsync(s.v[vi].progress, 0, (size_t)kMaxPasses * mb * 4, st));
+        for (int p = 0; p < ndir; p++) {
+            PassDesc &pd = P.pv[P.nPV++];
+            fill_pass(pd, p, w, h);
+            pd.C = s.v[vi].C; pd.L = s.v[vi].L[p]; pd.Lmin = s.v[vi].Lmin[p]; pd.arg = s.v[vi].arg[p];
+            pd.progress = s.v[vi].progress + (size_t)p * mb;
+            if (pd.nBands > P.maxBands) P.maxBands = pd.nBands;
+        }
+    }
+    P.P1 = P1; P.P2 = P2; P.next_item = s.next_item; P.abort_flag = ctx->abort_flag; P.lut = lut;
+    CK(cudaMemsetAsync(s.next_item, 0, 4, st));
+    int r = agg_launch(LPL, tsgm, P, ctx->sm_count, st);
+    if (r == -2) return fail(S2PB_ERR_UNSUPPORTED, "no aggregation kernel for %d labels per lane", LPL);
+    if (r != 0) return fail(S2PB_ERR_CUDA, "aggregation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->launches++;
+    return S2PB_OK;
+}
+
+template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t *cv, int w, int h, const short *lo, const short *hi,
+                                             int gmin, __half *C, int sm, cudaStream_t st)
+{
+    cost_kernel<LPL><<<sm * 8, 256, 0, st>>>(cu, cv, w, h, lo, hi, gmin, C);
+}
+template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStream_t st)
+{
+    wta_kernel<LPL><<<sm * 8, 256, 0, st>>>(P);
+}
+#define LPL_SWITCH(LPL, CALL)                                                             \
+    switch (LPL) {                                                                        \
+    case 1: { constexpr int K = 1; CALL; } break;   case 2: { constexpr int K = 2; CALL; } break;   \
+    case 3: { constexpr int K = 3; CALL; } break;   case 4: { constexpr int K = 4; CALL; } break;   \
+    case 5: { constexpr int K = 5; CALL; } break;   case 6: { constexpr int K = 6; CALL; } break;   \
+    case 8: { constexpr int K = 8; CALL; } break;   case 12: { constexpr int K = 12; CALL; } break; \
+    case 16: { constexpr int K = 16; CALL; } break;                                        \
+    default: return fail(S2PB_ERR_UNSUPPORTED, "unsupported labels-per-lane %d", LPL);     \
+    }
+
+static int launch_cost(s2pb_ctx *ctx, int LPL, const uint64_t *cu, const uint64_t *cv, int w, int h, const short *lo, const short *hi,
+                       int gmin, __half *C, cudaStream_t st)
+{
+    LPL_SWITCH(LPL, launch_cost_t<K>(cu, cv, w, h, lo, hi, gmin, C, ctx->sm_count, st));
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return S2PB_OK;
+}
+static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t st)
+{
+    LPL_SWITCH(LPL, launch_wta_t<K>(P, ctx->sm_count, st));
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return S2PB_OK;
+}
+
+static void fill_wta(WtaParams &P, const ViewWS &v, int ndir, int gmin, const s2pb_mgm_params *p, const float *lut, size_t npix)
+{
+    memset(&P, 0, sizeof P);
+    for (int d = 0; d < ndir; d++) { P.L[d] = v.L[d]; P.arg[d] = v.arg[d]; }
+    P.C = v.C; P.lo = v.lo; P.hi = v.hi; P.lut = lut;
+    P.ndir = ndir; P.gmin = gmin; P.fix_overcount = p->fix_overcount; P.refine = p->refine;
+    P.inv_zoom_div = 1.f; P.npix = npix; P.S = nullptr; P.Dout = 0;
+    P.disp = v.disp; P.cost = v.cost; P.conf = v.conf;
+}
+
+// ------------------------------------------------------------------ the matcher (device level)
+
+static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *d_im2, int w, int h, int dmin, int dmax,
+                       const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_dispR, cudaStream_t st)
+{
+    const size_t npix = (size_t)w * h;
+    const int n = (int)npix;
+    // label hull of each view (main_mgm.cc:178,207,210-216).  The no-data sentinel range
+    // [dmin, dmin+1] is inside the left hull; on the right it may stick out by one label.
+    int gminv[2] = {dmin, (-dmax < dmin) ? -dmax : dmin};
+    int gmaxv[2] = {dmax, (-dmin > dmin + 1) ? -dmin : dmin + 1};
+    int D = 0;
+    for (int vi = 0; vi < 2; vi++) { int d = gmaxv[vi] - gminv[vi] + 1; if (d > D) D = d; }
+    int LPL = lpl_for(D);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "disparity range of %d labels exceeds the 512 supported", D);
+    int rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir);
+    if (rc != S2PB_OK) return rc;
+
+    float lut_h[64];
+    const float *lut = nullptr;
+    if (cost_lut(p->census_win, lut_h)) {
+        CK(cudaMemcpyAsync(s.lut, lut_h, sizeof lut_h, cudaMemcpyHostToDevice, st));
+        lut = s.lut;
+    }
+    const float *im[2] = {d_im1, d_im2};
+    dim3 b2(32, 8);
+    s.timed = true;
+    CK(cudaEventRecord(s.ev[0], st));
+    // ---- census of both images on their NaN-free copies
+    for (int vi = 0; vi < 2; vi++) {
+        int lo_all = vi == 0 ? dmin : -dmax, hi_all = vi == 0 ? dmax : -dmin;
+        prepare_view_kernel<<<(n + 255) / 256, 256, 0, st>>>(im[vi], n, lo_all, hi_all, dmin, s.v[vi].img, s.v[vi].lo, s.v[vi].hi);
+        census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].img, w, h, p->census_win / 2, s.v[vi].census);
+        ctx->launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s.ev[1], st));
+    // ---- cost volumes: view 0 = left reference, view 1 = right reference (mgm_multiscale.cc:222,270)
+    for (int vi = 0; vi < 2; vi++) {
+        rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census, w, h, s.v[vi].lo, s.v[vi].hi, gminv[vi], s.v[vi].C, st);
+        if (rc != S2PB_OK) return rc;
+    }
+    CK(cudaEventRecord(s.ev[2], st));
+    // ---- 8-pass MGM of both views in one persistent launch
+    rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1, p->P2, p->ndir, p->tsgm, lut, st);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaEventRecord(s.ev[3], st));
+    // ---- WTA + consensus + sub-pixel
+    for (int vi = 0; vi < 2; vi++) {
+        WtaParams W;
+        fill_wta(W, s.v[vi], p->ndir, gminv[vi], p, lut, npix);
+        rc = launch_wta(ctx, LPL, W, st);
+        if (rc != S2PB_OK) return rc;
+    }
+    CK(cudaEventRecord(s.ev[4], st));
+    // ---- post filters (mgm_multiscale.cc:310-327), no-data restore (main_mgm.cc:231-236), mask
+    float *dl = s.v[0].disp, *dr = s.v[1].disp, *tl = s.v[0].tmp, *tr = s.v[1].tmp;
+    if (p->median > 0) {
+        median_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dl, tl, w, h, p->median);
+        median_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dr, tr, w, h, p->median);
+        ctx->launches += 2;
+        float *x = dl; dl = tl; tl = x; x = dr; dr = tr; tr = x;
+    }
+    float *outL = d_disp, *outR = d_dispR ? d_dispR : tr;
+    if (p->lr_mode == 1) {
+        lrcheck_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dr, dl, outR, w, h, p->lr_tau);
+        lrcheck_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dl, dr, outL, w, h, p->lr_tau);
+        ctx->launches += 2;
+    } else {
+        CK(cudaMemcpyAsync(outL, dl, npix * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(outR, dr, npix * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    nan_restore_kernel<<<(n + 255) / 256, 256, 0, st>>>(outL, d_im1, n);
+    nan_restore_kernel<<<(n + 255) / 256, 256, 0, st>>>(outR, d_im2, n);
+    ctx->launches += 2;
+    if (d_conf) CK(cudaMemcpyAsync(d_conf, s.v[0].conf, npix * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_mask) {
+        rejection_mask_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(outL, d_im1, d_im2, w, h, d_mask);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s.ev[5], st));
+    return S2PB_OK;
+}
+
+// wait for `ev` honouring timeout_ms; on expiry raise the abort flag so that the persistent
+// aggregation kernel drains, then report S2PB_ERR_TIMEOUT (-> subprocess.TimeoutExpired upstream).
+static int wait_with_timeout(s2pb_ctx *ctx, cudaStream_t st, int timeout_ms)
+{
+    if (timeout_ms <= 0) { CK(cudaStreamSynchronize(st)); return S2PB_OK; }
+    auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaSuccess) return S2PB_OK;
+        if (e != cudaErrorNotReady) return fail(S2PB_ERR_CUDA, "stream failed: %s", cudaGetErrorString(e));
+        auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > timeout_ms) {
+            *(volatile int *)ctx->abort_flag = 1;
+            cudaStreamSynchronize(st);
+            *(volatile int *)ctx->abort_flag = 0;
+            return fail(S2PB_ERR_TIMEOUT, "matcher exceeded timeout of %d ms", timeout_ms);
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+    }
+}
+
+extern "C" int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, const float *d_im2, int w, int h, int dmin, int dmax,
+                               const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_disp_right,
+                               void *stream)
+{
+    if (!ctx || !d_im1 || !d_im2 || !d_disp) return fail(S2PB_ERR_ARG, "null argument");
+    int rc = check_params(p, w, h, dmin, dmax);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if (slot < 0) return fail(S2PB_ERR_ARG, "negative slot");
+    rc = ensure_slots(ctx, slot + 1);
+    if (rc != S2PB_OK) return rc;
+    Slot &s = ctx->slots[slot];
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    rc = mgm_enqueue(ctx, s, d_im1, d_im2, w, h, dmin, dmax, p, d_disp, d_conf, d_mask, d_disp_right, st);
+    if (rc != S2PB_OK) return rc;
+    if (p->timeout_ms > 0) return wait_with_timeout(ctx, st, p->timeout_ms);
+    return S2PB_OK;
+}
+
+// stage the inputs of one tile through pinned memory and enqueue everything on the slot's stream
+static int mgm_host_enqueue(s2pb_ctx *ctx, Slot &s, const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+                            const s2pb_mgm_params *p, bool want_mask, bool want_right)
+{
+    size_t npix = (size_t)w * h;
+    int rc = slot_host_ensure(s, npix);
+    if (rc != S2PB_OK) return rc;
+    // size the workspace before touching d_in
+    int gmin1 = (-dmax < dmin) ? -dmax : dmin, gmax1 = (-dmin > dmin + 1) ? -dmin : dmin + 1;
+    int D = dmax - dmin + 1; if (gmax1 - gmin1 + 1 > D) D = gmax1 - gmin1 + 1;
+    int LPL = lpl_for(D);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "disparity range of %d labels exceeds the 512 supported", D);
+    rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir);
+    if (rc != S2PB_OK) return rc;
+    memcpy(s.h_in[0], im1, npix * 4);
+    memcpy(s.h_in[1], im2, npix * 4);
+    CK(cudaMemcpyAsync(s.d_in[0], s.h_in[0], npix * 4, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.d_in[1], s.h_in[1], npix * 4, cudaMemcpyHostToDevice, s.stream));
+    rc = mgm_enqueue(ctx, s, s.d_in[0], s.d_in[1], w, h, dmin, dmax, p, s.d_disp, s.d_conf, want_mask ? s.d_mask : nullptr,
+                     want_right ? s.d_dispR : nullptr, s.stream);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaMemcpyAsync(s.h_disp, s.d_disp, npix * 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(s.h_conf, s.d_conf, npix * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (want_mask) CK(cudaMemcpyAsync(s.h_mask, s.d_mask, npix, cudaMemcpyDeviceToHost, s.stream));
+    if (want_right) CK(cudaMemcpyAsync(s.h_dispR, s.d_dispR, npix * 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaEventRecord(s.done, s.stream));
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_mgm(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+                        const s2pb_mgm_params *p, float *disp, float *conf, uint8_t *mask, float *disp_right)
+{
+    if (!ctx || !im1 || !im2 || !disp || !conf) return fail(S2PB_ERR_ARG, "null argument");
+    int rc = check_params(p, w, h, dmin, dmax);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    rc = mgm_host_enqueue(ctx, s, im1, im2, w, h, dmin, dmax, p, mask != nullptr, disp_right != nullptr);
+    if (rc != S2PB_OK) return rc;
+    rc = wait_with_timeout(ctx, s.stream, p->timeout_ms);
+    if (rc != S2PB_OK) return rc;
+    size_t npix = (size_t)w * h;
+    memcpy(disp, s.h_disp, npix * 4);
+    memcpy(conf, s.h_conf, npix * 4);
+    if (mask) memcpy(mask, s.h_mask, npix);
+    if (disp_right) memcpy(disp_right, s.h_dispR, npix * 4);
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_reserve(s2pb_ctx *ctx, int nslots, int w, int h, int nlabels)
+{
+    if (!ctx || nslots < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    int LPL = lpl_for(nlabels);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "too many labels");
+    int rc = ensure_slots(ctx, nslots);
+    if (rc != S2PB_OK) return rc;
+    for (int i = 0; i < nslots; i++) {
+        rc = slot_ensure(ctx, ctx->slots[i], w, h, 32 * LPL, 8);
+        if (rc != S2PB_OK) return rc;
+        rc = slot_host_ensure(ctx->slots[i], (size_t)w * h);
+        if (rc != S2PB_OK) return rc;
+    }
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_mgm_batch(s2pb_ctx *ctx, int n, const float *const *im1, const float *const *im2, int w, int h, int dmin,
+                              int dmax, const s2pb_mgm_params *p, float *const *disp, float *const *conf, uint8_t *const *mask)
+{
+    if (!ctx || n < 0 || !im1 || !im2 || !disp || !conf) return fail(S2PB_ERR_ARG, "null argument");
+    int rc = check_params(p, w, h, dmin, dmax);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int ns = (int)ctx->slots.size();
+    const size_t npix = (size_t)w * h;
+    std::vector<int> inflight(ns, -1);
+    auto t0 = std::chrono::steady_clock::now();
+    auto collect = [&](int si) -> int {
+        Slot &s = ctx->slots[si];
+        int t = inflight[si];
+        if (t < 0) return S2PB_OK;
+        int left = 0;
+        if (p->timeout_ms > 0) {
+            auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+            left = (int)(p->timeout_ms * (long long)(n > 0 ? n : 1) - ms);
+            if (left < 1) left = 1;
+        }
+        int r = wait_with_timeout(ctx, s.stream, left);
+        if (r != S2PB_OK) return r;
+        memcpy(disp[t], s.h_disp, npix * 4);
+        memcpy(conf[t], s.h_conf, npix * 4);
+        if (mask && mask[t]) memcpy(mask[t], s.h_mask, npix);
+        inflight[si] = -1;
+        return S2PB_OK;
+    };
+    for (int t = 0; t < n; t++) {
+        int si = t % ns;
+        rc = collect(si);
+        if (rc != S2PB_OK) return rc;
+        rc = mgm_host_enqueue(ctx, ctx->slots[si], im1[t], im2[t], w, h, dmin, dmax, p, mask && mask[t], false);
+        if (rc != S2PB_OK) return rc;
+        inflight[si] = t;
+    }
+    for (int k = 0; k < ns; k++) {
+        rc = collect((n + k) % ns);
+        if (rc != S2PB_OK) return rc;
+    }
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_last_timings(s2pb_ctx *ctx, int slot, float ms[S2PB_T_COUNT])
+{
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !ms) return fail(S2PB_ERR_ARG, "bad argument");
+    Slot &s = ctx->slots[slot];
+    if (!s.timed) return fail(S2PB_ERR_ARG, "no timed call on this slot yet");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(s.ev[5]));
+    for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&ms[i], s.ev[i], s.ev[i + 1]));
+    CK(cudaEventElapsedTime(&ms[S2PB_T_TOTAL], s.ev[0], s.ev[5]));
+    return S2PB_OK;
+}
+
+// ------------------------------------------------------------------ stage-level entry points (host buffers)
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+    template <class T> T *as() { return (T *)p; }
+};
+#define ALLOC(buf, n) do { if ((buf).alloc(n) != 0) { cudaGetLastError(); return fail(S2PB_ERR_NOMEM, "cudaMalloc of %zu bytes failed", (size_t)(n)); } } while (0)
+
+extern "C" int s2pb_census(s2pb_ctx *ctx, const float *img, int w, int h, int win, uint64_t *codes)
+{
+    if (!ctx || !img || !codes || w < 1 || h < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    if (win != 3 && win != 5 && win != 7) return fail(S2PB_ERR_ARG, "census window must be 3, 5 or 7");
+    CK(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)w * h;
+    DevBuf a, b;
+    ALLOC(a, npix * 4); ALLOC(b, npix * 8);
+    cudaStream_t st = ctx->slots[0].stream;
+    CK(cudaMemcpyAsync(a.p, img, npix * 4, cudaMemcpyHostToDevice, st));
+    dim3 b2(32, 8);
+    census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(a.as<float>(), w, h, win / 2, b.as<uint64_t>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(codes, b.p, npix * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+static int upload_ranges(const int32_t *lo, const int32_t *hi, size_t npix, int gmin, int D, DevBuf &dlo, DevBuf &dhi, cudaStream_t st)
+{
+    std::vector<short> a(npix), b(npix);
+    for (size_t i = 0; i < npix; i++) {
+        if (lo[i] < gmin || hi[i] > gmin + D - 1 || lo[i] > hi[i]) return fail(S2PB_ERR_ARG, "range of pixel %zu outside the volume", i);
+        a[i] = (short)lo[i]; b[i] = (short)hi[i];
+    }
+    ALLOC(dlo, npix * 2); ALLOC(dhi, npix * 2);
+    CK(cudaMemcpyAsync(dlo.p, a.data(), npix * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dhi.p, b.data(), npix * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_costvolume(s2pb_ctx *ctx, const float *u, const float *v, int w, int h, const int32_t *lo, const int32_t *hi,
+                               int gmin, int D, int win, float *C)
+{
+    if (!ctx || !u || !v || !lo || !hi || !C || w < 1 || h < 1 || D < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    if (win != 3 && win != 5 && win != 7) return fail(S2PB_ERR_ARG, "census window must be 3, 5 or 7");
+    CK(cudaSetDevice(ctx->device));
+    int LPL = lpl_for(D);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "too many labels");
+    const int DP = 32 * LPL;
+    size_t npix = (size_t)w * h;
+    cudaStream_t st = ctx->slots[0].stream;
+    DevBuf du, dv, cu, cv, dlo, dhi, dC, dCf, dlut;
+    ALLOC(du, npix * 4); ALLOC(dv, npix * 4); ALLOC(cu, npix * 8); ALLOC(cv, npix * 8);
+    ALLOC(dC, npix * DP * 2); ALLOC(dCf, npix * D * 4); ALLOC(dlut, 256);
+    int rc = upload_ranges(lo, hi, npix, gmin, D, dlo, dhi, st);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaMemcpyAsync(du.p, u, npix * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv.p, v, npix * 4, cudaMemcpyHostToDevice, st));
+    dim3 b2(32, 8);
+    census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(du.as<float>(), w, h, win / 2, cu.as<uint64_t>());
+    census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dv.as<float>(), w, h, win / 2, cv.as<uint64_t>());
+    ctx->launches += 2;
+    rc = launch_cost(ctx, LPL, cu.as<uint64_t>(), cv.as<uint64_t>(), w, h, dlo.as<short>(), dhi.as<short>(), gmin, dC.as<__half>(), st);
+    if (rc != S2PB_OK) return rc;
+    float lut_h[64];
+    const float *lut = nullptr;
+    if (cost_lut(win, lut_h)) { CK(cudaMemcpyAsync(dlut.p, lut_h, 256, cudaMemcpyHostToDevice, st)); lut = dlut.as<float>(); }
+    size_t tot = npix * D;
+    unpack_cost_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dC.as<__half>(), npix, D, DP, lut, dCf.as<float>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(C, dCf.p, tot * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_aggregate(s2pb_ctx *ctx, const float *C, const int32_t *lo, const int32_t *hi, int w, int h, int gmin, int D,
+                              float P1, float P2, int ndir, int tsgm, int fix_overcount, float *S, float *disp, float *cost, float *conf)
+{
+    if (!ctx || !C || !lo || !hi || !disp || w < 2 || h < 2 || D < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    if (ndir != 2 && ndir != 4 && ndir != 8) return fail(S2PB_ERR_ARG, "ndir must be 2, 4 or 8");
+    if (tsgm < 1 || tsgm > 4) return fail(S2PB_ERR_ARG, "tsgm must be 1..4");
+    CK(cudaSetDevice(ctx->device));
+    int LPL = lpl_for(D);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "too many labels");
+    const int DP = 32 * LPL;
+    size_t npix = (size_t)w * h, tot = npix * D;
+    for (size_t i = 0; i < tot; i++) {   // the device slab stores costs as f16 (exact for census popcounts)
+        float c = C[i];
+        if (!(c == INFINITY || (c >= 0.f && c <= 2048.f && c == floorf(c))))
+            return fail(S2PB_ERR_UNSUPPORTED, "cost %g at %zu is not an integer in [0,2048] or +inf", c, i);
+    }
+    Slot &s = ctx->slots[0];
+    cudaStream_t st = s.stream;
+    int rc = slot_ensure(ctx, s, w, h, DP, ndir);
+    if (rc != S2PB_OK) return rc;
+    DevBuf dCf, dlo, dhi, dS;
+    ALLOC(dCf, tot * 4);
+    if (S) ALLOC(dS, tot * 4);
+    rc = upload_ranges(lo, hi, npix, gmin, D, dlo, dhi, st);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaMemcpyAsync(dCf.p, C, tot * 4, cudaMemcpyHostToDevice, st));
+    size_t totp = npix * DP;
+    pack_cost_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(dCf.as<float>(), npix, D, DP, s.v[0].C);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    rc = launch_aggregate(ctx, s, 1, w, h, LPL, P1, P2, ndir, tsgm, nullptr, st);
+    if (rc != S2PB_OK) return rc;
+    s2pb_mgm_params prm;
+    s2pb_default_params("mgm", &prm);
+    prm.fix_overcount = fix_overcount; prm.refine = 0;
+    WtaParams W;
+    fill_wta(W, s.v[0], ndir, gmin, &prm, nullptr, npix);
+    W.lo = dlo.as<short>(); W.hi = dhi.as<short>();
+    W.S = S ? dS.as<float>() : nullptr; W.Dout = D;
+    rc = launch_wta(ctx, LPL, W, st);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaMemcpyAsync(disp, s.v[0].disp, npix * 4, cudaMemcpyDeviceToHost, st));
+    if (cost) CK(cudaMemcpyAsync(cost, s.v[0].cost, npix * 4, cudaMemcpyDeviceToHost, st));
+    if (conf) CK(cudaMemcpyAsync(conf, s.v[0].conf, npix * 4, cudaMemcpyDeviceToHost, st));
+    if (S) CK(cudaMemcpyAsync(S, dS.p, tot * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_median(s2pb_ctx *ctx, const float *in, float *out, int w, int h, int radius)
+{
+    if (!ctx || !in || !out || w < 1 || h < 1 || radius < 0 || radius > 2) return fail(S2PB_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)w * h;
+    DevBuf a, b;
+    ALLOC(a, npix * 4); ALLOC(b, npix * 4);
+    cudaStream_t st = ctx->slots[0].stream;
+    CK(cudaMemcpyAsync(a.p, in, npix * 4, cudaMemcpyHostToDevice, st));
+    dim3 b2(32, 8);
+    median_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(a.as<float>(), b.as<float>(), w, h, radius);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, b.p, npix * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_rejection_mask(s2pb_ctx *ctx, const float *disp, const float *im1, const float *im2, int w, int h, uint8_t *mask)
+{
+    if (!ctx || !disp || !im1 || !im2 || !mask || w < 1 || h < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)w * h;
+    DevBuf a, b, c, m;
+    ALLOC(a, npix * 4); ALLOC(b, npix * 4); ALLOC(c, npix * 4); ALLOC(m, npix);
+    cudaStream_t st = ctx->slots[0].stream;
+    CK(cudaMemcpyAsync(a.p, disp, npix * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b.p, im1, npix * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c.p, im2, npix * 4, cudaMemcpyHostToDevice, st));
+    dim3 b2(32, 8);
+    rejection_mask_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(a.as<float>(), b.as<float>(), c.as<float>(), w, h, m.as<uint8_t>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(mask, m.p, npix, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh, const double H[9], float *dst, int dw, int dh)
+{
+    (void)ctx; (void)src; (void)sw; (void)sh; (void)H; (void)dst; (void)dw; (void)dh;
+    return fail(S2PB_ERR_UNSUPPORTED, "s2pb_homography is not implemented in this build");
+}

@@ -1,0 +1,187 @@
+"""numpy-level handle on the B200 stereo engine (one context per process and GPU).
+
+``Engine.mgm`` is the in-memory equivalent of what s2p obtains from the `mgm`
+subprocess plus ``create_rejection_mask`` (s2p/block_matching.py:18-32,155-188):
+rectified pair in, (disparity, consensus confidence, rejection mask) out.
+CUDA is initialised lazily in the calling process, so a forked
+``multiprocessing`` worker (s2p/parallel.py:80) creates its own context.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import MgmParams, S2pbError  # noqa: F401  (re-exported)
+
+
+def default_params(algo="mgm", **overrides):
+    p = MgmParams()
+    _lib.check(_lib.lib().s2pb_default_params(algo.encode(), ctypes.byref(p)))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown matcher parameter %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+def device_count():
+    return _lib.lib().s2pb_device_count()
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+class Engine:
+    def __init__(self, device=0):
+        L = _lib.lib()
+        self._L = L
+        self._ctx = L.s2pb_create(int(device))
+        if not self._ctx:
+            raise S2pbError(_lib.ERR_CUDA, L.s2pb_last_error().decode("utf-8", "replace"))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.s2pb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------------ matcher
+    def mgm(self, im1, im2, dmin, dmax, params=None, want_mask=True, want_right=False):
+        """-> dict(disp, conf, mask[, disp_right]) for one rectified pair (host arrays)."""
+        p = params or default_params("mgm")
+        im1, im2 = _f32(im1), _f32(im2)
+        if im1.shape != im2.shape or im1.ndim != 2:
+            raise ValueError("im1 and im2 must be 2-D arrays of the same shape")
+        h, w = im1.shape
+        disp = np.empty((h, w), np.float32)
+        conf = np.empty((h, w), np.float32)
+        mask = np.empty((h, w), np.uint8) if want_mask else None
+        right = np.empty((h, w), np.float32) if want_right else None
+        _lib.check(self._L.s2pb_mgm(
+            self._ctx, _fp(im1), _fp(im2), w, h, int(dmin), int(dmax), ctypes.byref(p), _fp(disp), _fp(conf),
+            mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if want_mask else None,
+            _fp(right) if want_right else None))
+        out = dict(disp=disp, conf=conf, mask=mask)
+        if want_right:
+            out["disp_right"] = right
+        return out
+
+    def mgm_batch(self, refs, secs, dmin, dmax, params=None, want_mask=True):
+        """n same-shaped pairs pipelined over the context's workspaces (s2pb_reserve first for overlap)."""
+        p = params or default_params("mgm")
+        n = len(refs)
+        refs = [_f32(a) for a in refs]
+        secs = [_f32(a) for a in secs]
+        h, w = refs[0].shape
+        disp = [np.empty((h, w), np.float32) for _ in range(n)]
+        conf = [np.empty((h, w), np.float32) for _ in range(n)]
+        mask = [np.empty((h, w), np.uint8) for _ in range(n)] if want_mask else None
+        arr = lambda xs: (ctypes.c_void_p * n)(*[x.ctypes.data for x in xs])
+        _lib.check(self._L.s2pb_mgm_batch(self._ctx, n, arr(refs), arr(secs), w, h, int(dmin), int(dmax), ctypes.byref(p),
+                                          arr(disp), arr(conf), arr(mask) if want_mask else None))
+        return disp, conf, mask
+
+    def mgm_device(self, slot, d_im1, d_im2, w, h, dmin, dmax, params, d_disp, d_conf=0, d_mask=0, d_right=0, stream=0):
+        """Device pointers in and out (integers, e.g. torch ``tensor.data_ptr()``); asynchronous on the slot's stream."""
+        _lib.check(self._L.s2pb_mgm_device(self._ctx, int(slot), d_im1, d_im2, int(w), int(h), int(dmin), int(dmax),
+                                           ctypes.byref(params), d_disp, d_conf or None, d_mask or None, d_right or None,
+                                           stream or None))
+
+    def reserve(self, nslots, w, h, nlabels):
+        _lib.check(self._L.s2pb_reserve(self._ctx, int(nslots), int(w), int(h), int(nlabels)))
+
+    def sync(self):
+        _lib.check(self._L.s2pb_sync(self._ctx))
+
+    def last_timings(self, slot=0):
+        ms = (ctypes.c_float * len(_lib.T_NAMES))()
+        _lib.check(self._L.s2pb_last_timings(self._ctx, int(slot), ms))
+        return dict(zip(_lib.T_NAMES, [float(x) for x in ms]))
+
+    def kernel_launches(self):
+        return int(self._L.s2pb_kernel_launches(self._ctx))
+
+    # ------------------------------------------------------------------ stages (parity tests)
+    def census(self, img, win=5):
+        img = _f32(img)
+        h, w = img.shape
+        out = np.empty((h, w), np.uint64)
+        _lib.check(self._L.s2pb_census(self._ctx, _fp(img), w, h, win, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        return out
+
+    def costvolume(self, u, v, lo, hi, gmin, D, win=5):
+        u, v = _f32(u), _f32(v)
+        h, w = u.shape
+        lo = np.ascontiguousarray(lo, np.int32)
+        hi = np.ascontiguousarray(hi, np.int32)
+        C = np.empty((h, w, D), np.float32)
+        ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        _lib.check(self._L.s2pb_costvolume(self._ctx, _fp(u), _fp(v), w, h, ip(lo), ip(hi), int(gmin), int(D), win, _fp(C)))
+        return C
+
+    def aggregate(self, C, lo, hi, gmin, P1=8.0, P2=32.0, ndir=8, tsgm=3, fix_overcount=1, want_S=True):
+        C = _f32(C)
+        h, w, D = C.shape
+        lo = np.ascontiguousarray(lo, np.int32)
+        hi = np.ascontiguousarray(hi, np.int32)
+        S = np.empty_like(C) if want_S else None
+        disp = np.empty((h, w), np.float32)
+        cost = np.empty((h, w), np.float32)
+        conf = np.empty((h, w), np.float32)
+        ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        _lib.check(self._L.s2pb_aggregate(self._ctx, _fp(C), ip(lo), ip(hi), w, h, int(gmin), D, P1, P2, ndir, tsgm,
+                                          fix_overcount, _fp(S) if want_S else None, _fp(disp), _fp(cost), _fp(conf)))
+        return S, disp, cost, conf
+
+    def median(self, img, radius=1):
+        img = _f32(img)
+        h, w = img.shape
+        out = np.empty_like(img)
+        _lib.check(self._L.s2pb_median(self._ctx, _fp(img), _fp(out), w, h, radius))
+        return out
+
+    def rejection_mask(self, disp, im1, im2):
+        disp, im1, im2 = _f32(disp), _f32(im1), _f32(im2)
+        h, w = disp.shape
+        mask = np.empty((h, w), np.uint8)
+        _lib.check(self._L.s2pb_rejection_mask(self._ctx, _fp(disp), _fp(im1), _fp(im2), w, h,
+                                               mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
+        return mask
+
+
+_engines = {}
+
+
+def get_engine(device=None):
+    """Per-process, per-device singleton.  ``device=None`` picks a GPU from the
+    multiprocessing worker identity (worker k -> GPU k mod n_gpu), which is how the
+    s2p process pool (s2p/parallel.py:80-98) is spread over the GPUs of a box."""
+    if device is None:
+        device = int(os.environ.get("S2PB_DEVICE", -1))
+        if device < 0:
+            import multiprocessing
+            ident = multiprocessing.current_process()._identity
+            n = max(1, device_count())
+            device = (ident[0] - 1) % n if ident else 0
+    key = (os.getpid(), device)
+    if key not in _engines:
+        _engines[key] = Engine(device)
+    return _engines[key]

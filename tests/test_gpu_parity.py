@@ -1,0 +1,130 @@
+"""GPU parity proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bit-exact for the integer WTA index, confidence, mask and -- because the
+device arithmetic follows the reference's float32 operation order -- for the sub-pixel map too
+(the contract only asks +-0.25 px; both are asserted, the tolerance stated here)."""
+import numpy as np
+import pytest
+
+from s2p_b200.synth import make_pair
+from util import nmismatch, same
+
+pytestmark = pytest.mark.gpu
+SUBPIX_TOL = 0.25  # px, BASELINE.json north_star
+
+
+def _ranges(h, w, dmin, dmax):
+    return np.full((h, w), dmin, np.int32), np.full((h, w), dmax, np.int32)
+
+
+@pytest.mark.parametrize("win", [5, 3, 7])
+def test_census(engine, oracle, win):
+    ref, _, _ = make_pair(61, 83, -8, 8, seed=11)
+    assert np.array_equal(engine.census(ref, win), oracle.port.census(ref, win))
+
+
+@pytest.mark.parametrize("win,dmin,dmax", [(5, -12, 11), (3, -5, 20), (7, -40, 2), (5, -64, 63)])
+def test_costvolume(engine, oracle, win, dmin, dmax):
+    h, w = 37, 150
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=3)
+    lo, hi = _ranges(h, w, dmin, dmax)
+    lo[5:9, 10:40] = dmin + 1            # ragged per-pixel ranges
+    hi[5:9, 10:40] = dmin + 3
+    D = dmax - dmin + 1
+    Cg = engine.costvolume(ref, sec, lo, hi, dmin, D, win)
+    Co = oracle.port.costvolume(ref, sec, lo, hi, dmin, D, win)
+    assert same(Cg, Co)
+
+
+@pytest.mark.parametrize("tsgm", [1, 2, 3, 4])
+@pytest.mark.parametrize("ndir", [8, 4])
+def test_aggregate(engine, oracle, tsgm, ndir):
+    h, w, dmin, dmax = 45, 70, -10, 13
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=5)
+    lo, hi = _ranges(h, w, dmin, dmax)
+    lo[20:24, 30:50] = dmin
+    hi[20:24, 30:50] = dmin + 1
+    D = dmax - dmin + 1
+    C = oracle.port.costvolume(ref, sec, lo, hi, dmin, D, 5)
+    So, do, co, fo = oracle.port.aggregate(C, lo, hi, dmin, 8.0, 32.0, ndir, tsgm)
+    Sg, dg, cg, fg = engine.aggregate(C, lo, hi, dmin, 8.0, 32.0, ndir, tsgm)
+    assert same(dg, do), "integer WTA index differs at %d pixels" % nmismatch(dg, do)
+    assert same(fg, fo), "consensus differs at %d pixels" % nmismatch(fg, fo)
+    assert same(Sg, So), "aggregated volume differs at %d voxels" % nmismatch(Sg, So)
+    assert same(cg, co)
+
+
+@pytest.mark.parametrize("shape,dmin,dmax,nanb,seed", [
+    ((64, 96), -12, 11, 0.0, 1),      # D=24  -> 1 label per lane
+    ((50, 81), -20, 30, 0.0, 2),      # D=51  -> 2
+    ((40, 130), -64, 63, 0.0, 3),     # D=128 -> 4
+    ((33, 140), -64, 63, 0.06, 4),    # no-data in both images: right hull sticks out -> 5
+    ((30, 200), -90, 70, 0.0, 5),     # D=161 -> 6
+    ((24, 260), -128, 127, 0.0, 6),   # D=256 -> 8
+    ((70, 45), 3, 19, 0.05, 7),       # positive range, more rows than columns, no-data
+])
+def test_mgm_end_to_end(engine, oracle, shape, dmin, dmax, nanb, seed):
+    h, w = shape
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=seed, nan_border=nanb)
+    from s2p_b200.engine import default_params
+    out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm"), want_mask=True, want_right=True)
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params())
+    m = oracle.port.rejection_mask(d, ref, sec)
+    both = np.isfinite(d) & np.isfinite(out["disp"])
+    assert np.array_equal(np.isnan(d), np.isnan(out["disp"]))
+    assert np.all(np.abs(d[both] - out["disp"][both]) <= SUBPIX_TOL)
+    assert same(out["disp"], d), "sub-pixel disparity not bit-exact at %d px" % nmismatch(out["disp"], d)
+    assert same(out["conf"], c), "confidence differs at %d px" % nmismatch(out["conf"], c)
+    assert same(out["disp_right"], dr)
+    assert np.array_equal(out["mask"], m)
+
+
+@pytest.mark.parametrize("kw", [dict(tsgm=4), dict(tsgm=2), dict(ndir=4), dict(census_win=3), dict(census_win=7),
+                                dict(median=0, lr_mode=0, refine=0), dict(median=2), dict(P1=4.0, P2=50.0)])
+def test_mgm_options(engine, oracle, kw):
+    h, w, dmin, dmax = 48, 90, -9, 14
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=21, nan_border=0.04)
+    from s2p_b200.engine import default_params
+    out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm", **kw), want_right=True)
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(**kw))
+    assert same(out["disp"], d), "disparity differs at %d px" % nmismatch(out["disp"], d)
+    assert same(out["conf"], c)
+    assert same(out["disp_right"], dr)
+
+
+def test_median_and_mask(engine, oracle):
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(40, 50)).astype(np.float32)
+    a[rng.random(a.shape) < 0.2] = np.nan
+    for r in (1, 2):
+        assert same(engine.median(a, r), oracle.port.median(a, r))
+    ref, sec, gt = make_pair(40, 50, -6, 6, seed=9, nan_border=0.1)
+    d = gt + rng.uniform(-0.5, 0.5, gt.shape).astype(np.float32)
+    d[rng.random(d.shape) < 0.1] = np.nan
+    assert np.array_equal(engine.rejection_mask(d, ref, sec), oracle.port.rejection_mask(d, ref, sec))
+
+
+def test_batch_matches_single(engine):
+    from s2p_b200.engine import default_params
+    h, w, dmin, dmax = 40, 64, -8, 7
+    pairs = [make_pair(h, w, dmin, dmax, seed=s)[:2] for s in range(5)]
+    engine.reserve(3, w, h, dmax - dmin + 1)
+    p = default_params("mgm")
+    disp, conf, mask = engine.mgm_batch([a for a, _ in pairs], [b for _, b in pairs], dmin, dmax, p)
+    for k, (a, b) in enumerate(pairs):
+        one = engine.mgm(a, b, dmin, dmax, p)
+        assert same(disp[k], one["disp"]) and same(conf[k], one["conf"]) and np.array_equal(mask[k], one["mask"])
+
+
+def test_timeout_and_errors(engine):
+    from s2p_b200 import _lib
+    from s2p_b200.engine import S2pbError, default_params
+    ref, sec, _ = make_pair(512, 512, -100, 100, seed=1)
+    with pytest.raises(S2pbError) as e:
+        engine.mgm(ref, sec, -100, 100, default_params("mgm", timeout_ms=1))
+    assert e.value.code == _lib.ERR_TIMEOUT
+    # the context stays usable after an aborted call
+    out = engine.mgm(ref[:64, :64], sec[:64, :64], -8, 8, default_params("mgm"))
+    assert np.isfinite(out["disp"]).any()
+    with pytest.raises(S2pbError) as e:
+        engine.mgm(ref, sec, 5, 5, default_params("mgm"))
+    assert e.value.code == _lib.ERR_ARG
