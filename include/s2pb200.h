@@ -91,11 +91,15 @@ int s2pb_mgm(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h,
 /* Same, device pointers on both sides, enqueued on `stream` (a cudaStream_t
  * passed as void*, NULL = the context's own stream) and NOT synchronised when
  * timeout_ms <= 0.  `slot` selects one of the context's workspaces
- * (0 <= slot < s2pb_num_slots) so that several tiles can be in flight. */
+ * (0 <= slot < s2pb_num_slots) so that several tiles can be in flight.
+ * nodata_hint: bit 1 = the secondary image may hold NaN pixels (the reference
+ * then gives them the label range [dmin, dmin+1], main_mgm.cc:214-216, which can
+ * widen the right view's volume); 0 = neither image holds NaN; < 0 = unknown, the
+ * library inspects the image (one stream synchronisation). */
 int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, const float *d_im2,
                     int w, int h, int dmin, int dmax, const s2pb_mgm_params *p,
                     float *d_disp, float *d_conf, uint8_t *d_mask, float *d_disp_right,
-                    void *stream);
+                    int nodata_hint, void *stream);
 
 /* n independent tiles of identical shape, pipelined over the context's slots
  * (pinned staging + H2D, compute, D2H overlap).  Arrays of n host pointers. */

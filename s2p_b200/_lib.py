@@ -44,7 +44,7 @@ _SIGNATURES = {
     "s2pb_default_params": (c_int, [c_char_p, POINTER(MgmParams)]),
     "s2pb_mgm": (c_int, [c_void_p, _f, _f, c_int, c_int, c_int, c_int, POINTER(MgmParams), _f, _f, POINTER(c_uint8), _f]),
     "s2pb_mgm_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(MgmParams),
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "s2pb_mgm_batch": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int,
                                POINTER(MgmParams), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
     "s2pb_reserve": (c_int, [c_void_p, c_int, c_int, c_int, c_int]),

@@ -7,16 +7,15 @@
 namespace s2pb {
 
 static constexpr int kLPL = S2PB_LPL;
-static constexpr size_t kSmem = (size_t)kNW * kRing * 32 * kLPL * sizeof(float) + (size_t)kNW * kRing * sizeof(float);
+static constexpr size_t kSmem = AggSmem<kLPL>::bytes;
 static constexpr int kCtaPerSm = (kLPL <= 4) ? 2 : 1;
 
 template <> int agg_configure_lpl<kLPL>()
 {
     cudaError_t e = cudaSuccess;
-    e = cudaFuncSetAttribute(aggregate_kernel<kLPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem); if (e) return -1;
-    e = cudaFuncSetAttribute(aggregate_kernel<kLPL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem); if (e) return -1;
-    e = cudaFuncSetAttribute(aggregate_kernel<kLPL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem); if (e) return -1;
-    e = cudaFuncSetAttribute(aggregate_kernel<kLPL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem); if (e) return -1;
+#define CFG(T, S) e = cudaFuncSetAttribute(aggregate_kernel<kLPL, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem); if (e) return -1;
+    CFG(1, false) CFG(2, false) CFG(3, false) CFG(4, false) CFG(1, true) CFG(2, true) CFG(3, true) CFG(4, true)
+#undef CFG
     return 0;
 }
 
@@ -27,13 +26,17 @@ template <> int agg_launch_lpl<kLPL>(int tsgm, const AggParams &P, int sm_count,
     int total = P.maxBands * P.nPV;
     if (grid > total) grid = total;
     dim3 block(kNW * 32);
+    const bool scaled = P.lut != nullptr;
+#define GO(T) do { if (scaled) aggregate_kernel<kLPL, T, true><<<grid, block, kSmem, st>>>(P); \
+                   else aggregate_kernel<kLPL, T, false><<<grid, block, kSmem, st>>>(P); } while (0)
     switch (tsgm) {
-    case 1: aggregate_kernel<kLPL, 1><<<grid, block, kSmem, st>>>(P); break;
-    case 2: aggregate_kernel<kLPL, 2><<<grid, block, kSmem, st>>>(P); break;
-    case 3: aggregate_kernel<kLPL, 3><<<grid, block, kSmem, st>>>(P); break;
-    case 4: aggregate_kernel<kLPL, 4><<<grid, block, kSmem, st>>>(P); break;
+    case 1: GO(1); break;
+    case 2: GO(2); break;
+    case 3: GO(3); break;
+    case 4: GO(4); break;
     default: return -2;
     }
+#undef GO
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

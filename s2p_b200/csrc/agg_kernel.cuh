@@ -161,6 +161,16 @@ __device__ __forceinline__ float cost_value(unsigned short hbits, const float *_
 // four neighbours -- A=(i-1,s) in-line, B=(i-1,s-1), Cn=(i,s-1), E=(i+1,s-1) -- listed in one of
 // two orders: type 0 (passes 0-3) = A,Cn,B,E ; type 1 (passes 4-7) = E,B,Cn,A.  TSGM takes
 // the first TSGM of them.
+//
+// Execution model.  A band = kNW consecutive scanlines = one CTA, one warp per scanline, lanes over
+// labels.  Scanline s trails scanline s-1 by SKEW pixels (1, or 2 when the neighbour E is used), the
+// CTA advances in lock step (one __syncthreads per pixel step) and a warp hands its aggregated vector
+// to the next scanline through a shared-memory ring.  Bands of one pass are chained through HBM: the
+// last scanline of band b-1 is what warp 0 of band b reads back (from L2) behind a release/acquire
+// progress counter.  Everything that comes from global memory -- the f16 costs of every scanline and
+// the previous band's vectors -- is staged into shared memory with cp.async kStage steps ahead, so no
+// global-memory latency sits on the lock-step critical path.  CTAs are persistent and pull
+// (band, pass-view) items from a global queue ordered band-major, which keeps the chain deadlock free.
 struct PassDesc {
     int nS, nI;
     long long base;
@@ -181,6 +191,71 @@ struct AggParams {
     const int *abort_flag;
     const float *lut;
 };
+
+constexpr int kStage = 8;     // cp.async pipeline depth (pixel steps)
+constexpr int kR0 = 16;       // slots of the previous-band ring (> kStage + 1: pixel 0 is staged ahead of the pipeline)
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// copy NBYTES (multiple of 16) from global to shared with the whole warp
+template <int NBYTES> __device__ __forceinline__ void warp_cp_async(void *smem, const void *gmem, int lane)
+{
+    constexpr int CH = NBYTES / 16;
+#pragma unroll
+    for (int q = 0; q < (CH + 31) / 32; q++) {
+        int c = lane + 32 * q;
+        if (CH % 32 == 0 || c < CH) cp_async16((char *)smem + 16 * c, (const char *)gmem + 16 * c);
+    }
+}
+// a lane's LPL f16 costs from shared memory (widest aligned access)
+template <int LPL> __device__ __forceinline__ HalfPack<LPL> lds_cost(const __half *p)
+{
+    HalfPack<LPL> r;
+    if constexpr (LPL % 8 == 0) {
+#pragma unroll
+        for (int q = 0; q < LPL / 8; q++) {
+            uint4 t = reinterpret_cast<const uint4 *>(p)[q];
+            unsigned w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) { r.h[8 * q + 2 * k] = w[k] & 0xffff; r.h[8 * q + 2 * k + 1] = w[k] >> 16; }
+        }
+    } else if constexpr (LPL % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < LPL / 4; q++) {
+            uint2 t = reinterpret_cast<const uint2 *>(p)[q];
+            r.h[4 * q] = t.x & 0xffff; r.h[4 * q + 1] = t.x >> 16; r.h[4 * q + 2] = t.y & 0xffff; r.h[4 * q + 3] = t.y >> 16;
+        }
+    } else if constexpr (LPL % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < LPL / 2; q++) {
+            unsigned t = reinterpret_cast<const unsigned *>(p)[q];
+            r.h[2 * q] = t & 0xffff; r.h[2 * q + 1] = t >> 16;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < LPL; q++) r.h[q] = reinterpret_cast<const unsigned short *>(p)[q];
+    }
+    return r;
+}
+// x / 3 with two fmas: bit-identical to IEEE division for every finite x >= 0
+// (exhaustively verified on the CPU: tests/test_host_logic.py::test_div3_trick)
+__device__ __forceinline__ float div3_exact(float x)
+{
+    const float r3 = 0.3333333432674407958984375f;   // RN(1/3)
+    float q0 = x * r3;
+    float r = fmaf(-3.0f, q0, x);
+    return fmaf(r, r3, q0);
+}
 
 template <int LPL> struct NbVec {
     float v[LPL];
@@ -203,9 +278,20 @@ template <int LPL> __device__ __forceinline__ float nb_term(const NbVec<LPL> &n,
     return fmin3f(n.v[e], v1, mP2) - n.m;
 }
 
-template <int LPL, int TSGM, int TYPE>
+// shared memory carve-up of one CTA (floats first, then halfs; every block 16-byte aligned)
+template <int LPL> struct AggSmem {
+    static constexpr int DP = 32 * LPL;
+    static constexpr size_t ring_off = 0;                                           // float [kNW][kRing][DP]
+    static constexpr size_t ringm_off = ring_off + sizeof(float) * kNW * kRing * DP; // float [kNW][kRing]
+    static constexpr size_t r0_off = ringm_off + sizeof(float) * kNW * kRing;        // float [kR0][DP]   previous band
+    static constexpr size_t r0m_off = r0_off + sizeof(float) * kR0 * DP;             // float [kR0]
+    static constexpr size_t cst_off = r0m_off + sizeof(float) * kR0;                 // half [kNW][kStage][DP]
+    static constexpr size_t bytes = cst_off + sizeof(__half) * kNW * kStage * DP;
+};
+
+template <int LPL, int TSGM, int TYPE, bool SCALED>
 __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1, float P2, const float *__restrict__ lut,
-                                         const int *abort_flag, float *ring, float *ringmin)
+                                         const int *abort_flag, unsigned char *smem)
 {
     constexpr int DP = 32 * LPL;
     constexpr bool useA = (TYPE == 0) ? true : (TSGM == 4);
@@ -215,6 +301,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     constexpr bool usePrev = useCn || useB || useE;
     constexpr int SKEW = useE ? 2 : 1;    // scanline s trails scanline s-1 by SKEW pixels
     constexpr int LEAD = useE ? 1 : 0;    // newest previous-scanline pixel needed at position i is i+LEAD
+    using SM = AggSmem<LPL>;
 
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int s = band * kNW + k;
@@ -223,67 +310,91 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     const bool from_global = (k == 0);                       // previous scanline belongs to the previous band
     const bool publish = live && (k == kNW - 1) && (s + 1 < pd.nS);
     const bool has_prev = usePrev && live && s > 0;
+    const bool stage_prev = has_prev && from_global;
     const long long rowbase = pd.base + (long long)s * pd.strideS;
     const long long prevbase = rowbase - pd.strideS;
+    float *ring = reinterpret_cast<float *>(smem + SM::ring_off);
+    float *ringm = reinterpret_cast<float *>(smem + SM::ringm_off);
+    float *r0 = reinterpret_cast<float *>(smem + SM::r0_off);
+    float *r0m = reinterpret_cast<float *>(smem + SM::r0m_off);
+    __half *cst = reinterpret_cast<__half *>(smem + SM::cst_off) + (size_t)k * kStage * DP;
     float *myring = ring + (size_t)k * kRing * DP;
-    float *myringmin = ringmin + k * kRing;
-    const float *srcring = ring + (size_t)(k - 1) * kRing * DP;      // only dereferenced when k > 0
-    const float *srcringmin = ringmin + (k - 1) * kRing;
+    float *myringm = ringm + k * kRing;
+    const float *srcring = from_global ? r0 : ring + (size_t)(k - 1) * kRing * DP;
+    const float *srcringm = from_global ? r0m : ringm + (k - 1) * kRing;
+    constexpr int SRCMASK_RING = kRing - 1, SRCMASK_R0 = kR0 - 1;
+    const int srcmask = from_global ? SRCMASK_R0 : SRCMASK_RING;
     const int *prev_progress = (band > 0) ? pd.progress + (band - 1) : nullptr;
     int avail = 0;                                            // cached progress of the previous band
 
-    NbVec<LPL> wA, wB, wC, wE, nxt;                           // window on the previous scanline + in-line neighbour
-#pragma unroll
-    for (int e = 0; e < LPL; e++) wA.v[e] = wB.v[e] = wC.v[e] = wE.v[e] = nxt.v[e] = 0.f;
-    wA.l = wA.r = wA.m = wB.l = wB.r = wB.m = wC.l = wC.r = wC.m = wE.l = wE.r = wE.m = nxt.l = nxt.r = nxt.m = 0.f;
-
-    // fetch pixel j of the previous scanline (vector + its minimum); edges are filled by the caller
-    auto fetch_prev = [&](int j, NbVec<LPL> &dst) {
-        if (from_global) {
-            while (avail < j + 1) {
+    // stage pixel `j` of this scanline's costs and (warp 0) pixel `j + LEAD` of the previous band's last scanline
+    auto stage = [&](int j) {
+        if (j < nI) {
+            const long long p = rowbase + (long long)j * pd.strideI;
+            warp_cp_async<DP * 2>(cst + (j & (kStage - 1)) * DP, pd.C + p * DP, lane);
+        }
+        const int jp = j + LEAD;
+        if (stage_prev && jp < nI) {
+            int spins = 0;
+            while (avail < jp + 1) {
                 avail = ld_acquire(prev_progress);
-                if (*(volatile const int *)abort_flag) break;
+                if (((++spins) & 1023) == 0 && *(volatile const int *)abort_flag) break;
             }
-            long long q = prevbase + (long long)j * pd.strideI;
-            ld_vec_cg<LPL>(pd.L + q * DP + lane * LPL, dst.v);
-            dst.m = __ldcg(pd.Lmin + q);
-        } else {
-            ld_vec<LPL>(srcring + (j & (kRing - 1)) * DP + lane * LPL, dst.v);
-            dst.m = srcringmin[j & (kRing - 1)];
+            const long long q = prevbase + (long long)jp * pd.strideI;
+            warp_cp_async<DP * 4>(r0 + (jp & (kR0 - 1)) * DP, pd.L + q * DP, lane);
+            if (lane == 0) cp_async4(r0m + (jp & (kR0 - 1)), pd.Lmin + q);
         }
     };
+    auto fetch_prev = [&](int j, NbVec<LPL> &dst) {
+        ld_vec<LPL>(srcring + (j & srcmask) * DP + lane * LPL, dst.v);
+        dst.m = srcringm[j & srcmask];
+        fill_edges<LPL>(dst, lane);
+    };
 
-    HalfPack<LPL> cnext;
-    if (live) cnext = ld_cost<LPL>(pd.C + rowbase * DP + lane * LPL);
+    NbVec<LPL> wA, wB, wC, wE;                                // window on the previous scanline + in-line neighbour
+#pragma unroll
+    for (int e = 0; e < LPL; e++) wA.v[e] = wB.v[e] = wC.v[e] = wE.v[e] = 0.f;
+    wA.l = wA.r = wA.m = wB.l = wB.r = wB.m = wC.l = wC.r = wC.m = wE.l = wE.r = wE.m = 0.f;
+
+    // prologue: kStage-1 groups in flight (group g holds the data of step g; warp 0 also stages pixel 0 of the previous band)
+    if (live) {
+        if (stage_prev && LEAD == 1) {
+            int spins = 0;
+            while (avail < 1) { avail = ld_acquire(prev_progress); if (((++spins) & 1023) == 0 && *(volatile const int *)abort_flag) break; }
+            warp_cp_async<DP * 4>(r0, pd.L + prevbase * DP, lane);
+            if (lane == 0) cp_async4(r0m, pd.Lmin + prevbase);
+        }
+#pragma unroll
+        for (int g = 0; g < kStage - 1; g++) { stage(g); cp_async_commit(); }
+    }
 
     const int nsteps = nI + (kNW - 1) * SKEW;
     for (int t = 0; t < nsteps; t++) {
         const int i = t - k * SKEW;
         if (live && i >= 0 && i < nI) {
             const long long p = rowbase + (long long)i * pd.strideI;
-            // ---- this pixel's matching costs (prefetched), prefetch the next pixel's
+            stage(i + kStage - 1);
+            cp_async_commit();
+            cp_async_wait<kStage - 1>();     // the group of step i has landed
+            __syncwarp();
+            // ---- this pixel's matching costs
             float c[LPL];
+            {
+                HalfPack<LPL> cp = lds_cost<LPL>(cst + (i & (kStage - 1)) * DP + lane * LPL);
 #pragma unroll
-            for (int e = 0; e < LPL; e++) c[e] = cost_value(cnext.h[e], lut);
-            if (i + 1 < nI) cnext = ld_cost<LPL>(pd.C + (p + pd.strideI) * DP + lane * LPL);
-
-            // ---- slide the window over the previous scanline
-            if (has_prev) {
-                if (from_global) {
-                    // software pipelined by one step: `nxt` was requested during the previous step
-                    if (i == 0) { if (LEAD == 1) { fetch_prev(0, wE); fill_edges<LPL>(wE, lane); } fetch_prev(LEAD, nxt); }
-                    wB = wC;
-                    if (useE) { wC = wE; wE = nxt; fill_edges<LPL>(wE, lane); }
-                    else { wC = nxt; fill_edges<LPL>(wC, lane); }
-                    if (i + 1 + LEAD < nI) fetch_prev(i + 1 + LEAD, nxt);
-                } else {
-                    if (i == 0 && LEAD == 1) { fetch_prev(0, wE); fill_edges<LPL>(wE, lane); }
-                    wB = wC;
-                    if (useE) { wC = wE; if (i + 1 < nI) { fetch_prev(i + 1, wE); fill_edges<LPL>(wE, lane); } }
-                    else { fetch_prev(i, wC); fill_edges<LPL>(wC, lane); }
+                for (int e = 0; e < LPL; e++) {
+                    float cc = __half2float(__ushort_as_half(cp.h[e]));
+                    if (SCALED) { if (cc < 64.f) cc = lut[(int)cc]; }
+                    c[e] = cc;
                 }
             }
-
+            // ---- slide the window over the previous scanline
+            if (has_prev) {
+                if (i == 0 && LEAD == 1) fetch_prev(0, wE);
+                wB = wC;
+                if (useE) { wC = wE; if (i + 1 < nI) fetch_prev(i + 1, wE); }
+                else fetch_prev(i, wC);
+            }
             // ---- the recursion (border pixels keep L = C: mgm_core.cc:953-960)
             float L[LPL];
             const bool border = (s == 0) || (i == 0) || (i == nI - 1);
@@ -306,12 +417,11 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
                         if (useCn) { float tt = nb_term<LPL>(wC, e, P1, mC); acc += tt; }
                         if (useA)  { float tt = nb_term<LPL>(wA, e, P1, mA); acc += tt; }
                     }
-                    if constexpr (TSGM == 3) acc = __fdiv_rn(acc, 3.0f);
+                    if constexpr (TSGM == 3) acc = div3_exact(acc);      // acc is finite and >= 0
                     if constexpr (TSGM == 4) acc = acc * 0.25f;
                     L[e] = c[e] + acc;
                 }
             }
-
             // ---- minimum, LAST arg-minimum (mgm_core.cc:1015-1019)
             float lm = L[0];
 #pragma unroll
@@ -321,7 +431,6 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
 #pragma unroll
             for (int e = 0; e < LPL; e++) if (L[e] == m) am = lane * LPL + e;
             am = __reduce_max_sync(0xffffffffu, am);
-
             // ---- hand over: registers (in-line), shared ring (next scanline of the band), HBM
 #pragma unroll
             for (int e = 0; e < LPL; e++) wA.v[e] = L[e];
@@ -329,7 +438,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             if (useA) fill_edges<LPL>(wA, lane);
             if (usePrev && k + 1 < kNW) {
                 st_vec<LPL>(myring + (i & (kRing - 1)) * DP + lane * LPL, L);
-                if (lane == 0) myringmin[i & (kRing - 1)] = m;
+                if (lane == 0) myringm[i & (kRing - 1)] = m;
             }
             st_vec<LPL>(pd.L + p * DP + lane * LPL, L);
             if (lane == 0) { pd.Lmin[p] = m; pd.arg[p] = (short)am; }
@@ -340,14 +449,13 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         }
         __syncthreads();
     }
+    cp_async_wait<0>();
 }
 
-template <int LPL, int TSGM>
+template <int LPL, int TSGM, bool SCALED>
 __global__ void __launch_bounds__(kNW * 32, (LPL <= 4) ? 2 : 1) aggregate_kernel(const __grid_constant__ AggParams P)
 {
-    extern __shared__ float smem[];
-    float *ring = smem;
-    float *ringmin = smem + (size_t)kNW * kRing * 32 * LPL;
+    extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_item;
     const int total = P.maxBands * P.nPV;
     for (;;) {
@@ -356,12 +464,11 @@ __global__ void __launch_bounds__(kNW * 32, (LPL <= 4) ? 2 : 1) aggregate_kernel
         const int item = s_item;
         __syncthreads();
         if (item >= total) return;
-        if (*(volatile const int *)P.abort_flag) return;
         const int band = item / P.nPV, pvi = item - band * P.nPV;
         const PassDesc &pd = P.pv[pvi];
         if (band >= pd.nBands) continue;
-        if (pd.type == 0) run_band<LPL, TSGM, 0>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, ring, ringmin);
-        else run_band<LPL, TSGM, 1>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, ring, ringmin);
+        if (pd.type == 0) run_band<LPL, TSGM, 0, SCALED>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, smem);
+        else run_band<LPL, TSGM, 1, SCALED>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, smem);
     }
 }
 

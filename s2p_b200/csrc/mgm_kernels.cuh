@@ -40,6 +40,14 @@ __global__ void prepare_view_kernel(const float *__restrict__ in, int n, int lo_
     hi[i] = (short)(isn ? sentinel + 1 : hi_all);
 }
 
+// does the image hold a NaN?  (sizes the right view's label hull, see plan_labels in s2pb200.cu)
+__global__ void has_nan_kernel(const float *__restrict__ in, int n, int *flag)
+{
+    bool f = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f |= isnan(in[i]);
+    if (__any_sync(0xffffffffu, f) && (threadIdx.x & 31) == 0) *(volatile int *)flag = 1;
+}
+
 // ------------------------------------------------------------------ cost volume
 
 // One warp per pixel.  mgm_costvolume.cc:140-172: label o of pixel (x,y) compares census

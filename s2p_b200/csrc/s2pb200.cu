@@ -77,6 +77,7 @@ struct s2pb_ctx {
     int sm_count = 148;
     std::vector<Slot> slots;
     int *abort_flag = nullptr;     // pinned + mapped: the host raises it on timeout
+    int *scratch_flag = nullptr;   // pinned + mapped: device -> host one-word answers
     long long launches = 0;
 };
 
@@ -205,10 +206,11 @@ extern "C" s2pb_ctx *s2pb_create(int device)
     s2pb_ctx *ctx = new s2pb_ctx;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaHostAlloc((void **)&ctx->abort_flag, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&ctx->abort_flag, 2 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
         fail(S2PB_ERR_CUDA, "cudaHostAlloc failed"); delete ctx; return nullptr;
     }
-    *ctx->abort_flag = 0;
+    ctx->scratch_flag = ctx->abort_flag + 1;
+    ctx->abort_flag[0] = ctx->abort_flag[1] = 0;
     ctx->slots.resize(1);
     if (slot_init(ctx, ctx->slots[0]) != S2PB_OK) { delete ctx; return nullptr; }
     if (agg_configure() != 0) { fail(S2PB_ERR_CUDA, "cudaFuncSetAttribute failed for the aggregation kernels"); delete ctx; return nullptr; }
@@ -303,9 +305,21 @@ static bool cost_lut(int win, float lut[64])
     return !identity;
 }
 
-struct ViewJob {
-    int gmin, D;
-};
+// Label hull of each view (main_mgm.cc:178,207,210-216).  The no-data sentinel range [dmin, dmin+1]
+// always lies inside the left hull; on the right view it only matters when the secondary image
+// really holds no-data pixels, and then it may stick out of [-dmax, -dmin].
+static int plan_labels(int dmin, int dmax, bool sec_has_nodata, int gminv[2], int gmaxv[2])
+{
+    gminv[0] = dmin; gmaxv[0] = dmax;
+    gminv[1] = -dmax; gmaxv[1] = -dmin;
+    if (sec_has_nodata) {
+        if (dmin < gminv[1]) gminv[1] = dmin;
+        if (dmin + 1 > gmaxv[1]) gmaxv[1] = dmin + 1;
+    }
+    int D = 0;
+    for (int vi = 0; vi < 2; vi++) { int d = gmaxv[vi] - gminv[vi] + 1; if (d > D) D = d; }
+    return lpl_for(D);
+}
 
 static void fill_pass(PassDesc &pd, int pass, int w, int h)
 {
@@ -398,18 +412,21 @@ static void fill_wta(WtaParams &P, const ViewWS &v, int ndir, int gmin, const s2
 // ------------------------------------------------------------------ the matcher (device level)
 
 static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *d_im2, int w, int h, int dmin, int dmax,
-                       const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_dispR, cudaStream_t st)
+                       const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_dispR, cudaStream_t st,
+                       int nodata_hint)
 {
     const size_t npix = (size_t)w * h;
     const int n = (int)npix;
-    // label hull of each view (main_mgm.cc:178,207,210-216).  The no-data sentinel range
-    // [dmin, dmin+1] is inside the left hull; on the right it may stick out by one label.
-    int gminv[2] = {dmin, (-dmax < dmin) ? -dmax : dmin};
-    int gmaxv[2] = {dmax, (-dmin > dmin + 1) ? -dmin : dmin + 1};
-    int D = 0;
-    for (int vi = 0; vi < 2; vi++) { int d = gmaxv[vi] - gminv[vi] + 1; if (d > D) D = d; }
-    int LPL = lpl_for(D);
-    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "disparity range of %d labels exceeds the 512 supported", D);
+    if (nodata_hint < 0) {     // unknown: look (costs one stream synchronisation)
+        *ctx->scratch_flag = 0;
+        has_nan_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_im2, n, ctx->scratch_flag);
+        ctx->launches++;
+        CK(cudaStreamSynchronize(st));
+        nodata_hint = *(volatile int *)ctx->scratch_flag ? 3 : 0;
+    }
+    int gminv[2], gmaxv[2];
+    int LPL = plan_labels(dmin, dmax, (nodata_hint & 2) != 0, gminv, gmaxv);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "disparity range [%d,%d] needs more than the 512 labels supported", dmin, dmax);
     int rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir);
     if (rc != S2PB_OK) return rc;
 
@@ -503,7 +520,7 @@ static int wait_with_timeout(s2pb_ctx *ctx, cudaStream_t st, int timeout_ms)
 
 extern "C" int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, const float *d_im2, int w, int h, int dmin, int dmax,
                                const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_disp_right,
-                               void *stream)
+                               int nodata_hint, void *stream)
 {
     if (!ctx || !d_im1 || !d_im2 || !d_disp) return fail(S2PB_ERR_ARG, "null argument");
     int rc = check_params(p, w, h, dmin, dmax);
@@ -514,7 +531,7 @@ extern "C" int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, cons
     if (rc != S2PB_OK) return rc;
     Slot &s = ctx->slots[slot];
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
-    rc = mgm_enqueue(ctx, s, d_im1, d_im2, w, h, dmin, dmax, p, d_disp, d_conf, d_mask, d_disp_right, st);
+    rc = mgm_enqueue(ctx, s, d_im1, d_im2, w, h, dmin, dmax, p, d_disp, d_conf, d_mask, d_disp_right, st, nodata_hint);
     if (rc != S2PB_OK) return rc;
     if (p->timeout_ms > 0) return wait_with_timeout(ctx, st, p->timeout_ms);
     return S2PB_OK;
@@ -527,19 +544,25 @@ static int mgm_host_enqueue(s2pb_ctx *ctx, Slot &s, const float *im1, const floa
     size_t npix = (size_t)w * h;
     int rc = slot_host_ensure(s, npix);
     if (rc != S2PB_OK) return rc;
+    // copy into the pinned staging block, noticing no-data pixels of the secondary image on the way
+    memcpy(s.h_in[0], im1, npix * 4);
+    bool sec_nodata = false;
+    {
+        float *dst = s.h_in[1];
+        unsigned acc = 0;
+        for (size_t i = 0; i < npix; i++) { float v = im2[i]; dst[i] = v; acc |= (unsigned)(v != v); }
+        sec_nodata = acc != 0;
+    }
     // size the workspace before touching d_in
-    int gmin1 = (-dmax < dmin) ? -dmax : dmin, gmax1 = (-dmin > dmin + 1) ? -dmin : dmin + 1;
-    int D = dmax - dmin + 1; if (gmax1 - gmin1 + 1 > D) D = gmax1 - gmin1 + 1;
-    int LPL = lpl_for(D);
-    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "disparity range of %d labels exceeds the 512 supported", D);
+    int gminv[2], gmaxv[2];
+    int LPL = plan_labels(dmin, dmax, sec_nodata, gminv, gmaxv);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "disparity range [%d,%d] needs more than the 512 labels supported", dmin, dmax);
     rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir);
     if (rc != S2PB_OK) return rc;
-    memcpy(s.h_in[0], im1, npix * 4);
-    memcpy(s.h_in[1], im2, npix * 4);
     CK(cudaMemcpyAsync(s.d_in[0], s.h_in[0], npix * 4, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.d_in[1], s.h_in[1], npix * 4, cudaMemcpyHostToDevice, s.stream));
     rc = mgm_enqueue(ctx, s, s.d_in[0], s.d_in[1], w, h, dmin, dmax, p, s.d_disp, s.d_conf, want_mask ? s.d_mask : nullptr,
-                     want_right ? s.d_dispR : nullptr, s.stream);
+                     want_right ? s.d_dispR : nullptr, s.stream, sec_nodata ? 2 : 0);
     if (rc != S2PB_OK) return rc;
     CK(cudaMemcpyAsync(s.h_disp, s.d_disp, npix * 4, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaMemcpyAsync(s.h_conf, s.d_conf, npix * 4, cudaMemcpyDeviceToHost, s.stream));

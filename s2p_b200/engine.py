@@ -99,11 +99,14 @@ class Engine:
                                           arr(disp), arr(conf), arr(mask) if want_mask else None))
         return disp, conf, mask
 
-    def mgm_device(self, slot, d_im1, d_im2, w, h, dmin, dmax, params, d_disp, d_conf=0, d_mask=0, d_right=0, stream=0):
-        """Device pointers in and out (integers, e.g. torch ``tensor.data_ptr()``); asynchronous on the slot's stream."""
+    def mgm_device(self, slot, d_im1, d_im2, w, h, dmin, dmax, params, d_disp, d_conf=0, d_mask=0, d_right=0,
+                   nodata_hint=-1, stream=0):
+        """Device pointers in and out (integers, e.g. torch ``tensor.data_ptr()``); asynchronous on the slot's
+        stream (or ``stream``).  nodata_hint: 0 = no NaN in the images, 2 = the secondary image may hold NaN,
+        -1 = let the library look (one stream synchronisation)."""
         _lib.check(self._L.s2pb_mgm_device(self._ctx, int(slot), d_im1, d_im2, int(w), int(h), int(dmin), int(dmax),
                                            ctypes.byref(params), d_disp, d_conf or None, d_mask or None, d_right or None,
-                                           stream or None))
+                                           int(nodata_hint), stream or None))
 
     def reserve(self, nslots, w, h, nlabels):
         _lib.check(self._L.s2pb_reserve(self._ctx, int(nslots), int(w), int(h), int(nlabels)))
