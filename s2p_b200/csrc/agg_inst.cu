@@ -41,3 +41,4 @@ template <> int agg_launch_lpl<kLPL>(int tsgm, const AggParams &P, int sm_count,
 }
 
 }  // namespace s2pb
+static_assert(s2pb::AggSmem<S2PB_LPL>::bytes <= 227 * 1024, "aggregation CTA exceeds the 227 KB of shared memory of an sm_100 SM");

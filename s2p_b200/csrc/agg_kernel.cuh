@@ -192,8 +192,12 @@ struct AggParams {
     const float *lut;
 };
 
-constexpr int kStage = 8;     // cp.async pipeline depth (pixel steps)
-constexpr int kR0 = 16;       // slots of the previous-band ring (> kStage + 1: pixel 0 is staged ahead of the pipeline)
+// cp.async pipeline depth in pixel steps (kStage) and slots of the previous-band ring (kR0 > kStage + 1,
+// because pixel 0 is staged ahead of the pipeline); shallower for the widest volumes so the CTA fits 227 KB
+template <int LPL> struct StageCfg {
+    static constexpr int kStage = (LPL <= 12) ? 8 : 2;
+    static constexpr int kR0 = (LPL <= 12) ? 16 : 4;
+};
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -281,6 +285,7 @@ template <int LPL> __device__ __forceinline__ float nb_term(const NbVec<LPL> &n,
 // shared memory carve-up of one CTA (floats first, then halfs; every block 16-byte aligned)
 template <int LPL> struct AggSmem {
     static constexpr int DP = 32 * LPL;
+    static constexpr int kStage = StageCfg<LPL>::kStage, kR0 = StageCfg<LPL>::kR0;
     static constexpr size_t ring_off = 0;                                           // float [kNW][kRing][DP]
     static constexpr size_t ringm_off = ring_off + sizeof(float) * kNW * kRing * DP; // float [kNW][kRing]
     static constexpr size_t r0_off = ringm_off + sizeof(float) * kNW * kRing;        // float [kR0][DP]   previous band
@@ -302,6 +307,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     constexpr int SKEW = useE ? 2 : 1;    // scanline s trails scanline s-1 by SKEW pixels
     constexpr int LEAD = useE ? 1 : 0;    // newest previous-scanline pixel needed at position i is i+LEAD
     using SM = AggSmem<LPL>;
+    constexpr int kStage = SM::kStage, kR0 = SM::kR0;
 
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int s = band * kNW + k;
