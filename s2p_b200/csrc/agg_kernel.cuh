@@ -294,6 +294,25 @@ template <int LPL> struct AggSmem {
     static constexpr size_t bytes = cst_off + sizeof(__half) * kNW * kStage * DP;
 };
 
+// smem address (32-bit, shared state space) helpers for cp.async
+__device__ __forceinline__ void cp_async16_s(unsigned sa, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4_s(unsigned sa, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+template <int NBYTES> __device__ __forceinline__ void warp_cp_async_s(unsigned sa, const char *gmem, int lane)
+{
+    constexpr int CH = NBYTES / 16;
+#pragma unroll
+    for (int q = 0; q < (CH + 31) / 32; q++) {
+        int c = lane + 32 * q;
+        if (CH % 32 == 0 || c < CH) cp_async16_s(sa + 16 * c, gmem + 16 * c);
+    }
+}
+
 template <int LPL, int TSGM, int TYPE, bool SCALED>
 __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1, float P2, const float *__restrict__ lut,
                                          const int *abort_flag, unsigned char *smem)
@@ -306,12 +325,14 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     constexpr bool usePrev = useCn || useB || useE;
     constexpr int SKEW = useE ? 2 : 1;    // scanline s trails scanline s-1 by SKEW pixels
     constexpr int LEAD = useE ? 1 : 0;    // newest previous-scanline pixel needed at position i is i+LEAD
+    constexpr int U = useE ? 3 : 2;       // the window registers rotate with period U: the step loop is unrolled by U
     using SM = AggSmem<LPL>;
     constexpr int kStage = SM::kStage, kR0 = SM::kR0;
 
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int s = band * kNW + k;
     const int nI = pd.nI;
+    const long long strideI = pd.strideI;
     const bool live = s < pd.nS;
     const bool from_global = (k == 0);                       // previous scanline belongs to the previous band
     const bool publish = live && (k == kNW - 1) && (s + 1 < pd.nS);
@@ -319,74 +340,86 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     const bool stage_prev = has_prev && from_global;
     const long long rowbase = pd.base + (long long)s * pd.strideS;
     const long long prevbase = rowbase - pd.strideS;
+
+    // ---- shared memory (32-bit shared-space addresses for cp.async, generic pointers for ld/st)
+    const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
     float *ring = reinterpret_cast<float *>(smem + SM::ring_off);
     float *ringm = reinterpret_cast<float *>(smem + SM::ringm_off);
-    float *r0 = reinterpret_cast<float *>(smem + SM::r0_off);
-    float *r0m = reinterpret_cast<float *>(smem + SM::r0m_off);
-    __half *cst = reinterpret_cast<__half *>(smem + SM::cst_off) + (size_t)k * kStage * DP;
-    float *myring = ring + (size_t)k * kRing * DP;
+    float *myring = ring + (size_t)k * kRing * DP + lane * LPL;
     float *myringm = ringm + k * kRing;
-    const float *srcring = from_global ? r0 : ring + (size_t)(k - 1) * kRing * DP;
-    const float *srcringm = from_global ? r0m : ringm + (k - 1) * kRing;
-    constexpr int SRCMASK_RING = kRing - 1, SRCMASK_R0 = kR0 - 1;
-    const int srcmask = from_global ? SRCMASK_R0 : SRCMASK_RING;
+    const float *srcring = (from_global ? reinterpret_cast<float *>(smem + SM::r0_off) : ring + (size_t)(k - 1) * kRing * DP) + lane * LPL;
+    const float *srcringm = from_global ? reinterpret_cast<float *>(smem + SM::r0m_off) : ringm + (k - 1) * kRing;
+    const int srcmask = from_global ? (kR0 - 1) : (kRing - 1);
+    const __half *cst = reinterpret_cast<__half *>(smem + SM::cst_off) + (size_t)k * kStage * DP + lane * LPL;
+    const unsigned cst_s = smem_s + (unsigned)SM::cst_off + (unsigned)(k * kStage * DP * 2);
+    const unsigned r0_s = smem_s + (unsigned)SM::r0_off, r0m_s = smem_s + (unsigned)SM::r0m_off;
+
+    // ---- global memory cursors (advance by one pixel of the scanline per step)
+    const long long cstep = strideI * (DP * 2), lstep = strideI * (DP * 4);
+    const char *c_stage = reinterpret_cast<const char *>(pd.C + rowbase * DP);            // next pixel to stage (costs)
+    const char *p_stage = reinterpret_cast<const char *>(pd.L + prevbase * DP);           // next previous-band pixel to stage
+    const float *pm_stage = pd.Lmin + prevbase;
+    char *l_out = reinterpret_cast<char *>(pd.L + rowbase * DP + lane * LPL);             // this pixel's output vector
+    long long p_cur = rowbase;                                                             // this pixel's index
+    int j_stage = 0, jp_stage = 0;                                                         // indices of the two staging cursors
+
     const int *prev_progress = (band > 0) ? pd.progress + (band - 1) : nullptr;
     int avail = 0;                                            // cached progress of the previous band
 
-    // stage pixel `j` of this scanline's costs and (warp 0) pixel `j + LEAD` of the previous band's last scanline
-    auto stage = [&](int j) {
-        if (j < nI) {
-            const long long p = rowbase + (long long)j * pd.strideI;
-            warp_cp_async<DP * 2>(cst + (j & (kStage - 1)) * DP, pd.C + p * DP, lane);
+    auto stage_cost = [&]() {            // stage pixel j_stage of this scanline's costs
+        if (j_stage < nI) {
+            warp_cp_async_s<DP * 2>(cst_s + (unsigned)((j_stage & (kStage - 1)) * (DP * 2)), c_stage, lane);
+            c_stage += cstep;
         }
-        const int jp = j + LEAD;
-        if (stage_prev && jp < nI) {
+        j_stage++;
+    };
+    auto stage_prevband = [&]() {        // (warp 0) stage pixel jp_stage of the previous band's last scanline
+        if (stage_prev && jp_stage < nI) {
             int spins = 0;
-            while (avail < jp + 1) {
+            while (avail < jp_stage + 1) {
                 avail = ld_acquire(prev_progress);
                 if (((++spins) & 1023) == 0 && *(volatile const int *)abort_flag) break;
             }
-            const long long q = prevbase + (long long)jp * pd.strideI;
-            warp_cp_async<DP * 4>(r0 + (jp & (kR0 - 1)) * DP, pd.L + q * DP, lane);
-            if (lane == 0) cp_async4(r0m + (jp & (kR0 - 1)), pd.Lmin + q);
+            const unsigned slot = (unsigned)(jp_stage & (kR0 - 1));
+            warp_cp_async_s<DP * 4>(r0_s + slot * (DP * 4), p_stage, lane);
+            if (lane == 0) cp_async4_s(r0m_s + slot * 4, pm_stage);
+            p_stage += lstep;
+            pm_stage += strideI;
         }
+        jp_stage++;
     };
     auto fetch_prev = [&](int j, NbVec<LPL> &dst) {
-        ld_vec<LPL>(srcring + (j & srcmask) * DP + lane * LPL, dst.v);
-        dst.m = srcringm[j & srcmask];
+        const int slot = j & srcmask;
+        ld_vec<LPL>(srcring + slot * DP, dst.v);
+        dst.m = srcringm[slot];
         fill_edges<LPL>(dst, lane);
     };
 
-    NbVec<LPL> wA, wB, wC, wE;                                // window on the previous scanline + in-line neighbour
+    NbVec<LPL> wA, x0, x1, x2;                                // in-line neighbour + rotating window on the previous scanline
 #pragma unroll
-    for (int e = 0; e < LPL; e++) wA.v[e] = wB.v[e] = wC.v[e] = wE.v[e] = 0.f;
-    wA.l = wA.r = wA.m = wB.l = wB.r = wB.m = wC.l = wC.r = wC.m = wE.l = wE.r = wE.m = 0.f;
+    for (int e = 0; e < LPL; e++) wA.v[e] = x0.v[e] = x1.v[e] = x2.v[e] = 0.f;
+    wA.l = wA.r = wA.m = x0.l = x0.r = x0.m = x1.l = x1.r = x1.m = x2.l = x2.r = x2.m = 0.f;
 
-    // prologue: kStage-1 groups in flight (group g holds the data of step g; warp 0 also stages pixel 0 of the previous band)
+    // prologue: kStage-1 groups in flight; group g holds costs(g) and previous-band pixel g+LEAD (+ pixel 0 when LEAD = 1)
     if (live) {
-        if (stage_prev && LEAD == 1) {
-            int spins = 0;
-            while (avail < 1) { avail = ld_acquire(prev_progress); if (((++spins) & 1023) == 0 && *(volatile const int *)abort_flag) break; }
-            warp_cp_async<DP * 4>(r0, pd.L + prevbase * DP, lane);
-            if (lane == 0) cp_async4(r0m, pd.Lmin + prevbase);
-        }
+        if (LEAD == 1) stage_prevband();
 #pragma unroll
-        for (int g = 0; g < kStage - 1; g++) { stage(g); cp_async_commit(); }
+        for (int g = 0; g < kStage - 1; g++) { stage_cost(); stage_prevband(); cp_async_commit(); }
     }
 
-    const int nsteps = nI + (kNW - 1) * SKEW;
-    for (int t = 0; t < nsteps; t++) {
+    // one lock-step pixel step; wB / wC / wE are the window registers in their role for this step
+    auto step = [&](const int t, NbVec<LPL> &wB, NbVec<LPL> &wC, NbVec<LPL> &wE) {
         const int i = t - k * SKEW;
         if (live && i >= 0 && i < nI) {
-            const long long p = rowbase + (long long)i * pd.strideI;
-            stage(i + kStage - 1);
+            stage_cost();
+            stage_prevband();
             cp_async_commit();
             cp_async_wait<kStage - 1>();     // the group of step i has landed
             __syncwarp();
             // ---- this pixel's matching costs
             float c[LPL];
             {
-                HalfPack<LPL> cp = lds_cost<LPL>(cst + (i & (kStage - 1)) * DP + lane * LPL);
+                HalfPack<LPL> cp = lds_cost<LPL>(cst + (i & (kStage - 1)) * DP);
 #pragma unroll
                 for (int e = 0; e < LPL; e++) {
                     float cc = __half2float(__ushort_as_half(cp.h[e]));
@@ -394,38 +427,35 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
                     c[e] = cc;
                 }
             }
-            // ---- slide the window over the previous scanline
+            // ---- newest pixel of the previous scanline enters the window
             if (has_prev) {
-                if (i == 0 && LEAD == 1) fetch_prev(0, wE);
-                wB = wC;
-                if (useE) { wC = wE; if (i + 1 < nI) fetch_prev(i + 1, wE); }
+                if (useE) { if (i == 0) fetch_prev(0, wC); if (i + 1 < nI) fetch_prev(i + 1, wE); }
                 else fetch_prev(i, wC);
             }
-            // ---- the recursion (border pixels keep L = C: mgm_core.cc:953-960)
+            // ---- the recursion; border pixels keep L = C (mgm_core.cc:953-960)
             float L[LPL];
             const bool border = (s == 0) || (i == 0) || (i == nI - 1);
-            if (border) {
-#pragma unroll
-                for (int e = 0; e < LPL; e++) L[e] = c[e];
-            } else {
+            {
                 const float mA = wA.m + P2, mB = wB.m + P2, mC = wC.m + P2, mE = wE.m + P2;
 #pragma unroll
                 for (int e = 0; e < LPL; e++) {
-                    float acc = 0.f;
+                    float acc;
                     if constexpr (TYPE == 0) {
-                        if (useA)  { float tt = nb_term<LPL>(wA, e, P1, mA); acc += (TSGM == 2) ? tt * 0.5f : tt; }
+                        acc = nb_term<LPL>(wA, e, P1, mA);
+                        if (TSGM == 2) acc *= 0.5f;
                         if (useCn) { float tt = nb_term<LPL>(wC, e, P1, mC); acc += (TSGM == 2) ? tt * 0.5f : tt; }
                         if (useB)  { float tt = nb_term<LPL>(wB, e, P1, mB); acc += tt; }
                         if (useE)  { float tt = nb_term<LPL>(wE, e, P1, mE); acc += tt; }
                     } else {
-                        if (useE)  { float tt = nb_term<LPL>(wE, e, P1, mE); acc += (TSGM == 2) ? tt * 0.5f : tt; }
+                        acc = nb_term<LPL>(wE, e, P1, mE);
+                        if (TSGM == 2) acc *= 0.5f;
                         if (useB)  { float tt = nb_term<LPL>(wB, e, P1, mB); acc += (TSGM == 2) ? tt * 0.5f : tt; }
                         if (useCn) { float tt = nb_term<LPL>(wC, e, P1, mC); acc += tt; }
                         if (useA)  { float tt = nb_term<LPL>(wA, e, P1, mA); acc += tt; }
                     }
-                    if constexpr (TSGM == 3) acc = div3_exact(acc);      // acc is finite and >= 0
+                    if constexpr (TSGM == 3) acc = div3_exact(acc);      // acc is finite and >= 0 on interior pixels
                     if constexpr (TSGM == 4) acc = acc * 0.25f;
-                    L[e] = c[e] + acc;
+                    L[e] = border ? c[e] : c[e] + acc;
                 }
             }
             // ---- minimum, LAST arg-minimum (mgm_core.cc:1015-1019)
@@ -442,18 +472,33 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             for (int e = 0; e < LPL; e++) wA.v[e] = L[e];
             wA.m = m;
             if (useA) fill_edges<LPL>(wA, lane);
-            if (usePrev && k + 1 < kNW) {
-                st_vec<LPL>(myring + (i & (kRing - 1)) * DP + lane * LPL, L);
-                if (lane == 0) myringm[i & (kRing - 1)] = m;
+            if (usePrev) st_vec<LPL>(myring + (i & (kRing - 1)) * DP, L);
+            st_vec<LPL>(reinterpret_cast<float *>(l_out), L);
+            if (lane == 0) {
+                if (usePrev) myringm[i & (kRing - 1)] = m;
+                pd.Lmin[p_cur] = m;
+                pd.arg[p_cur] = (short)am;
             }
-            st_vec<LPL>(pd.L + p * DP + lane * LPL, L);
-            if (lane == 0) { pd.Lmin[p] = m; pd.arg[p] = (short)am; }
+            l_out += lstep;
+            p_cur += strideI;
             if (publish && (((i + 1) % kPublish) == 0 || i == nI - 1)) {
                 __syncwarp();
                 if (lane == 0) st_release(pd.progress + band, i + 1);
             }
         }
         __syncthreads();
+    };
+
+    const int nsteps = nI + (kNW - 1) * SKEW;
+    for (int t = 0; t < nsteps; t += U) {
+        if constexpr (U == 2) {          // window: C = newest, B = the one before
+            step(t, x1, x0, x2);
+            step(t + 1, x0, x1, x2);
+        } else {                         // window: E = newest, then C, then B
+            step(t, x1, x2, x0);
+            step(t + 1, x2, x0, x1);
+            step(t + 2, x0, x1, x2);
+        }
     }
     cp_async_wait<0>();
 }
