@@ -25,7 +25,7 @@ template <> int agg_launch_lpl<kLPL>(int tsgm, const AggParams &P, int sm_count,
     int grid = sm_count * kCtaPerSm;
     int total = P.maxBands * P.nPV;
     if (grid > total) grid = total;
-    dim3 block(kNW * 32);
+    dim3 block(kAggThreads);
     const bool scaled = P.lut != nullptr;
 #define GO(T) do { if (scaled) aggregate_kernel<kLPL, T, true><<<grid, block, kSmem, st>>>(P); \
                    else aggregate_kernel<kLPL, T, false><<<grid, block, kSmem, st>>>(P); } while (0)

@@ -31,8 +31,10 @@ namespace s2pb {
 
 constexpr int kMaxPasses = 8;
 constexpr int kMaxPV = 16;    // pass-views handled by one aggregation launch (2 views x 8 passes)
-constexpr int kNW = 16;       // warps per CTA = scanlines per band
-constexpr int kRing = 4;      // ring slots per warp for handing vectors to the next scanline
+constexpr int kNW = 16;       // scanlines per band
+constexpr int kNWC = 8;       // warps per CTA, two scanlines each
+constexpr int kAggThreads = kNWC * 32;
+constexpr int kRing = 4;      // ring slots per compute warp for handing vectors to the next warp
 constexpr int kPublish = 8;   // a band publishes its progress every kPublish pixels
 
 // ------------------------------------------------------------------ small helpers
@@ -162,15 +164,17 @@ __device__ __forceinline__ float cost_value(unsigned short hbits, const float *_
 // two orders: type 0 (passes 0-3) = A,Cn,B,E ; type 1 (passes 4-7) = E,B,Cn,A.  TSGM takes
 // the first TSGM of them.
 //
-// Execution model.  A band = kNW consecutive scanlines = one CTA, one warp per scanline, lanes over
-// labels.  Scanline s trails scanline s-1 by SKEW pixels (1, or 2 when the neighbour E is used), the
-// CTA advances in lock step (one __syncthreads per pixel step) and a warp hands its aggregated vector
-// to the next scanline through a shared-memory ring.  Bands of one pass are chained through HBM: the
-// last scanline of band b-1 is what warp 0 of band b reads back (from L2) behind a release/acquire
-// progress counter.  Everything that comes from global memory -- the f16 costs of every scanline and
-// the previous band's vectors -- is staged into shared memory with cp.async kStage steps ahead, so no
-// global-memory latency sits on the lock-step critical path.  CTAs are persistent and pull
-// (band, pass-view) items from a global queue ordered band-major, which keeps the chain deadlock free.
+// Execution model.  A band = kNW (16) consecutive scanlines = one CTA of kNWC (8) warps; lanes run over
+// labels.  Scanline s trails scanline s-1 by SKEW pixels (1, or 2 when the neighbour E is used).  A warp
+// owns TWO adjacent scanlines: the lower one reads the upper one's last results straight from registers,
+// the two pixels of a step are independent instruction streams (ILP 2), and only every second scanline
+// boundary goes through a shared-memory ring to the next warp.  The CTA advances in lock step, one
+// __syncthreads per pixel step.  Everything that comes from global memory -- the f16 costs of the warp's
+// two scanlines (one 16-byte cp.async per lane and step) and, for the band's first scanline, the previous
+// band's aggregated vectors (re-read from L2 behind a release/acquire progress counter) -- is staged into
+// shared memory kStage-1 steps ahead, so no global-memory latency sits on the lock-step critical path.
+// CTAs are persistent and pull (band, pass-view) items from a global queue ordered band-major, which
+// keeps the chain of bands deadlock free.
 struct PassDesc {
     int nS, nI;
     long long base;
@@ -179,8 +183,7 @@ struct PassDesc {
     int nBands;
     const __half *C;
     float *L;
-    float *Lmin;
-    short *arg;
+    float *Lmin;     // minima of the band-closing scanlines only (read back by the next band)
     int *progress;   // [nBands] pixels of the band's last scanline visible in global memory
 };
 struct AggParams {
@@ -286,11 +289,11 @@ template <int LPL> __device__ __forceinline__ float nb_term(const NbVec<LPL> &n,
 template <int LPL> struct AggSmem {
     static constexpr int DP = 32 * LPL;
     static constexpr int kStage = StageCfg<LPL>::kStage, kR0 = StageCfg<LPL>::kR0;
-    static constexpr size_t ring_off = 0;                                           // float [kNW][kRing][DP]
-    static constexpr size_t ringm_off = ring_off + sizeof(float) * kNW * kRing * DP; // float [kNW][kRing]
-    static constexpr size_t r0_off = ringm_off + sizeof(float) * kNW * kRing;        // float [kR0][DP]   previous band
-    static constexpr size_t r0m_off = r0_off + sizeof(float) * kR0 * DP;             // float [kR0]
-    static constexpr size_t cst_off = r0m_off + sizeof(float) * kR0;                 // half [kNW][kStage][DP]
+    static constexpr size_t ring_off = 0;                                            // float [kNWC][kRing][DP]
+    static constexpr size_t ringm_off = ring_off + sizeof(float) * kNWC * kRing * DP; // float [kNWC][kRing]
+    static constexpr size_t r0_off = ringm_off + sizeof(float) * kNWC * kRing;        // float [kR0][DP]   previous band
+    static constexpr size_t r0m_off = r0_off + sizeof(float) * kR0 * DP;              // float [kR0]
+    static constexpr size_t cst_off = r0m_off + sizeof(float) * kR0;                  // half [kNW][kStage][DP]
     static constexpr size_t bytes = cst_off + sizeof(__half) * kNW * kStage * DP;
 };
 
@@ -325,186 +328,214 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     constexpr bool usePrev = useCn || useB || useE;
     constexpr int SKEW = useE ? 2 : 1;    // scanline s trails scanline s-1 by SKEW pixels
     constexpr int LEAD = useE ? 1 : 0;    // newest previous-scanline pixel needed at position i is i+LEAD
-    constexpr int U = useE ? 3 : 2;       // the window registers rotate with period U: the step loop is unrolled by U
+    constexpr int U = useE ? 3 : 2;       // window / history registers rotate with period U: the step loop is unrolled by U
     using SM = AggSmem<LPL>;
-    constexpr int kStage = SM::kStage, kR0 = SM::kR0;
+    constexpr int kStage = SM::kStage, kR0 = SM::kR0, S = kStage - 1;
+    constexpr int CH = 4 * LPL;           // 16-byte chunks of one pixel's f16 cost vector
 
-    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-    const int s = band * kNW + k;
     const int nI = pd.nI;
-    const long long strideI = pd.strideI;
-    const bool live = s < pd.nS;
-    const bool from_global = (k == 0);                       // previous scanline belongs to the previous band
-    const bool publish = live && (k == kNW - 1) && (s + 1 < pd.nS);
-    const bool has_prev = usePrev && live && s > 0;
-    const bool stage_prev = has_prev && from_global;
-    const long long rowbase = pd.base + (long long)s * pd.strideS;
-    const long long prevbase = rowbase - pd.strideS;
+    const int nsteps = (nI + (kNW - 1) * SKEW + U - 1) / U * U;
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
 
-    // ---- shared memory (32-bit shared-space addresses for cp.async, generic pointers for ld/st)
+    // ---- this warp's two scanlines: A (upper) and B = A + 1
+    const int sA = band * kNW + 2 * k;
+    const bool liveA = sA < pd.nS, liveB = sA + 1 < pd.nS;
+    const long long strideI = pd.strideI;
+    const bool prevA = usePrev && liveA && sA > 0;           // scanline A has a previous scanline (B always has A)
+    const bool from_r0 = (k == 0);                           // ... which belongs to the previous band
+    const bool publish = liveB && (k == kNWC - 1) && (sA + 2 < pd.nS);
+    const long long rowbaseA = pd.base + (long long)sA * pd.strideS;
+
     const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
     float *ring = reinterpret_cast<float *>(smem + SM::ring_off);
     float *ringm = reinterpret_cast<float *>(smem + SM::ringm_off);
     float *myring = ring + (size_t)k * kRing * DP + lane * LPL;
     float *myringm = ringm + k * kRing;
-    const float *srcring = (from_global ? reinterpret_cast<float *>(smem + SM::r0_off) : ring + (size_t)(k - 1) * kRing * DP) + lane * LPL;
-    const float *srcringm = from_global ? reinterpret_cast<float *>(smem + SM::r0m_off) : ringm + (k - 1) * kRing;
-    const int srcmask = from_global ? (kR0 - 1) : (kRing - 1);
-    const __half *cst = reinterpret_cast<__half *>(smem + SM::cst_off) + (size_t)k * kStage * DP + lane * LPL;
-    const unsigned cst_s = smem_s + (unsigned)SM::cst_off + (unsigned)(k * kStage * DP * 2);
+    const float *srcring = (from_r0 ? reinterpret_cast<float *>(smem + SM::r0_off) : ring + (size_t)(k - 1) * kRing * DP) + lane * LPL;
+    const float *srcringm = from_r0 ? reinterpret_cast<float *>(smem + SM::r0m_off) : ringm + (k - 1) * kRing;
+    const int srcmask = from_r0 ? (kR0 - 1) : (kRing - 1);
+    const __half *cstA = reinterpret_cast<__half *>(smem + SM::cst_off) + (size_t)(2 * k) * kStage * DP + lane * LPL;
+    const __half *cstB = cstA + kStage * DP;
+
+    // ---- staging cursors.  Costs: lanes 0-15 copy scanline A, lanes 16-31 scanline B, 16 bytes each.
+    const int rsel = lane >> 4, q16 = lane & 15;
+    const bool live_st = rsel ? liveB : liveA;
+    const char *csrc = reinterpret_cast<const char *>(pd.C + (rowbaseA + (long long)rsel * pd.strideS) * DP) + 16 * q16;
+    const long long cstep = strideI * (DP * 2);
+    const unsigned cdst = smem_s + (unsigned)SM::cst_off + (unsigned)((2 * k + rsel) * kStage * DP * 2 + 16 * q16);
+    int jc = 0;                                               // next pixel of my scanline to stage
+    //      previous band's last scanline (warp 0 only)
+    const bool stage_prev = prevA && from_r0;
+    const long long prevbase = rowbaseA - pd.strideS;
+    const char *psrc = reinterpret_cast<const char *>(pd.L + prevbase * DP);
+    const float *pmsrc = pd.Lmin + prevbase;
+    const long long lstepb = strideI * (DP * 4);
     const unsigned r0_s = smem_s + (unsigned)SM::r0_off, r0m_s = smem_s + (unsigned)SM::r0m_off;
-
-    // ---- global memory cursors (advance by one pixel of the scanline per step)
-    const long long cstep = strideI * (DP * 2), lstep = strideI * (DP * 4);
-    const char *c_stage = reinterpret_cast<const char *>(pd.C + rowbase * DP);            // next pixel to stage (costs)
-    const char *p_stage = reinterpret_cast<const char *>(pd.L + prevbase * DP);           // next previous-band pixel to stage
-    const float *pm_stage = pd.Lmin + prevbase;
-    char *l_out = reinterpret_cast<char *>(pd.L + rowbase * DP + lane * LPL);             // this pixel's output vector
-    long long p_cur = rowbase;                                                             // this pixel's index
-    int j_stage = 0, jp_stage = 0;                                                         // indices of the two staging cursors
-
     const int *prev_progress = (band > 0) ? pd.progress + (band - 1) : nullptr;
-    int avail = 0;                                            // cached progress of the previous band
+    int jp = 0, avail = 0;
 
-    auto stage_cost = [&]() {            // stage pixel j_stage of this scanline's costs
-        if (j_stage < nI) {
-            warp_cp_async_s<DP * 2>(cst_s + (unsigned)((j_stage & (kStage - 1)) * (DP * 2)), c_stage, lane);
-            c_stage += cstep;
+    auto stage_cost = [&]() {            // stage pixel jc of my scanline's costs
+        if (live_st && jc < nI) {
+            const unsigned d = cdst + (unsigned)((jc & (kStage - 1)) * (DP * 2));
+#pragma unroll
+            for (int q = 0; q < (CH + 15) / 16; q++)
+                if (CH % 16 == 0 || q16 + 16 * q < CH) cp_async16_s(d + 256 * q, csrc + 256 * q);
+            csrc += cstep;
         }
-        j_stage++;
+        jc++;
     };
-    auto stage_prevband = [&]() {        // (warp 0) stage pixel jp_stage of the previous band's last scanline
-        if (stage_prev && jp_stage < nI) {
-            int spins = 0;
-            while (avail < jp_stage + 1) {
-                avail = ld_acquire(prev_progress);
-                if (((++spins) & 1023) == 0 && *(volatile const int *)abort_flag) break;
+    auto stage_prevband = [&]() {        // (warp 0) stage pixel jp of the previous band's last scanline
+        if (stage_prev) {
+            if (jp < nI) {
+                int spins = 0;
+                while (avail < jp + 1) {
+                    avail = ld_acquire(prev_progress);
+                    if (((++spins) & 1023) == 0 && *(volatile const int *)abort_flag) break;
+                }
+                const unsigned slot = (unsigned)(jp & (kR0 - 1));
+                warp_cp_async_s<DP * 4>(r0_s + slot * (DP * 4), psrc, lane);
+                if (lane == 0) cp_async4_s(r0m_s + slot * 4, pmsrc);
+                psrc += lstepb;
+                pmsrc += strideI;
             }
-            const unsigned slot = (unsigned)(jp_stage & (kR0 - 1));
-            warp_cp_async_s<DP * 4>(r0_s + slot * (DP * 4), p_stage, lane);
-            if (lane == 0) cp_async4_s(r0m_s + slot * 4, pm_stage);
-            p_stage += lstep;
-            pm_stage += strideI;
+            jp++;
         }
-        jp_stage++;
     };
+
+    // ---- global output cursors
+    const long long lstep = strideI * DP;                    // floats per pixel step along the scanline
+    float *outA = pd.L + rowbaseA * DP + lane * LPL;
+    float *outB = outA + (long long)pd.strideS * DP;
+    float *lminB = pd.Lmin + rowbaseA + pd.strideS;          // only the band's last scanline publishes its minima
+
     auto fetch_prev = [&](int j, NbVec<LPL> &dst) {
         const int slot = j & srcmask;
         ld_vec<LPL>(srcring + slot * DP, dst.v);
         dst.m = srcringm[slot];
         fill_edges<LPL>(dst, lane);
     };
-
-    NbVec<LPL> wA, x0, x1, x2;                                // in-line neighbour + rotating window on the previous scanline
+    auto load_cost = [&](const __half *p, float (&c)[LPL]) {
+        HalfPack<LPL> cp = lds_cost<LPL>(p);
 #pragma unroll
-    for (int e = 0; e < LPL; e++) wA.v[e] = x0.v[e] = x1.v[e] = x2.v[e] = 0.f;
-    wA.l = wA.r = wA.m = x0.l = x0.r = x0.m = x1.l = x1.r = x1.m = x2.l = x2.r = x2.m = 0.f;
-
-    // prologue: kStage-1 groups in flight; group g holds costs(g) and previous-band pixel g+LEAD (+ pixel 0 when LEAD = 1)
-    if (live) {
-        if (LEAD == 1) stage_prevband();
+        for (int e = 0; e < LPL; e++) {
+            float cc = __half2float(__ushort_as_half(cp.h[e]));
+            if (SCALED) { if (cc < 64.f) cc = lut[(int)cc]; }
+            c[e] = cc;
+        }
+    };
+    // L = C + (sum of the neighbours' terms) / TSGM in the reference's order; border pixels keep L = C
+    auto recurse = [&](const float (&c)[LPL], const NbVec<LPL> &nA, const NbVec<LPL> &nB, const NbVec<LPL> &nC,
+                       const NbVec<LPL> &nE, bool border, float (&L)[LPL]) {
+        const float mA = nA.m + P2, mB = nB.m + P2, mC = nC.m + P2, mE = nE.m + P2;
 #pragma unroll
-        for (int g = 0; g < kStage - 1; g++) { stage_cost(); stage_prevband(); cp_async_commit(); }
-    }
+        for (int e = 0; e < LPL; e++) {
+            float acc;
+            if constexpr (TYPE == 0) {
+                acc = nb_term<LPL>(nA, e, P1, mA);
+                if (TSGM == 2) acc *= 0.5f;
+                if (useCn) { float tt = nb_term<LPL>(nC, e, P1, mC); acc += (TSGM == 2) ? tt * 0.5f : tt; }
+                if (useB)  { float tt = nb_term<LPL>(nB, e, P1, mB); acc += tt; }
+                if (useE)  { float tt = nb_term<LPL>(nE, e, P1, mE); acc += tt; }
+            } else {
+                acc = nb_term<LPL>(nE, e, P1, mE);
+                if (TSGM == 2) acc *= 0.5f;
+                if (useB)  { float tt = nb_term<LPL>(nB, e, P1, mB); acc += (TSGM == 2) ? tt * 0.5f : tt; }
+                if (useCn) { float tt = nb_term<LPL>(nC, e, P1, mC); acc += tt; }
+                if (useA)  { float tt = nb_term<LPL>(nA, e, P1, mA); acc += tt; }
+            }
+            if constexpr (TSGM == 3) acc = div3_exact(acc);      // acc is finite and >= 0 on interior pixels
+            if constexpr (TSGM == 4) acc = acc * 0.25f;
+            L[e] = border ? c[e] : c[e] + acc;
+        }
+    };
+    auto vec_min = [&](const float (&L)[LPL]) {
+        float lm = L[0];
+#pragma unroll
+        for (int e = 1; e < LPL; e++) lm = fminf(lm, L[e]);
+        return warp_min_f32(lm);
+    };
 
-    // one lock-step pixel step; wB / wC / wE are the window registers in their role for this step
-    auto step = [&](const int t, NbVec<LPL> &wB, NbVec<LPL> &wC, NbVec<LPL> &wE) {
-        const int i = t - k * SKEW;
-        if (live && i >= 0 && i < nI) {
-            stage_cost();
-            stage_prevband();
-            cp_async_commit();
-            cp_async_wait<kStage - 1>();     // the group of step i has landed
+    NbVec<LPL> x0, x1, x2, h0, h1, h2, wAB;                   // window on A's previous scanline, A's last results, B's last result
+#pragma unroll
+    for (int e = 0; e < LPL; e++) x0.v[e] = x1.v[e] = x2.v[e] = h0.v[e] = h1.v[e] = h2.v[e] = wAB.v[e] = 0.f;
+    x0.l = x0.r = x0.m = x1.l = x1.r = x1.m = x2.l = x2.r = x2.m = 0.f;
+    h0.l = h0.r = h0.m = h1.l = h1.r = h1.m = h2.l = h2.r = h2.m = wAB.l = wAB.r = wAB.m = 0.f;
+
+    // prologue: S groups in flight; group g holds costs(g) and previous-band pixel g+LEAD (+ pixel 0 when LEAD = 1)
+    if (LEAD == 1) stage_prevband();
+#pragma unroll 1
+    for (int g = 0; g < S; g++) { stage_cost(); stage_prevband(); cp_async_commit(); }
+
+    // One lock-step pixel step.  Roles at step t: (xB, xC, xE) = window on A's previous scanline at A's
+    // pixel-1, pixel, pixel+1; hNew = A's result of U steps ago (B's "B" neighbour; overwritten with A's new
+    // result at the end of the step), hC / hE = A's results of U-1.. / 1 steps ago.
+    auto step = [&](const int t, NbVec<LPL> &xB, NbVec<LPL> &xC, NbVec<LPL> &xE, NbVec<LPL> &hNew, NbVec<LPL> &hC, NbVec<LPL> &hE) {
+        const int iA = t - 2 * k * SKEW, iB = iA - SKEW;
+        const bool actA = liveA && iA >= 0 && iA < nI, actB = liveB && iB >= 0 && iB < nI;
+        NbVec<LPL> &inlineA = useE ? hE : hC;                 // A's result of the previous step
+        if (iA - rsel * SKEW >= 0) stage_cost();              // my scanline is at pixel jc - S: stage pixel jc
+        if (iA >= 0) stage_prevband();
+        cp_async_commit();
+        if (actA || actB) {
+            cp_async_wait<S>();                               // the groups of this step's pixels have landed
             __syncwarp();
-            // ---- this pixel's matching costs
-            float c[LPL];
-            {
-                HalfPack<LPL> cp = lds_cost<LPL>(cst + (i & (kStage - 1)) * DP);
-#pragma unroll
-                for (int e = 0; e < LPL; e++) {
-                    float cc = __half2float(__ushort_as_half(cp.h[e]));
-                    if (SCALED) { if (cc < 64.f) cc = lut[(int)cc]; }
-                    c[e] = cc;
-                }
+            float cA[LPL], cB[LPL], LA[LPL], LB[LPL];
+            load_cost(cstA + (iA & (kStage - 1)) * DP, cA);
+            load_cost(cstB + (iB & (kStage - 1)) * DP, cB);
+            if (prevA && actA) {
+                if (useE) { if (iA == 0) fetch_prev(0, xC); if (iA + 1 < nI) fetch_prev(iA + 1, xE); }
+                else fetch_prev(iA, xC);
             }
-            // ---- newest pixel of the previous scanline enters the window
-            if (has_prev) {
-                if (useE) { if (i == 0) fetch_prev(0, wC); if (i + 1 < nI) fetch_prev(i + 1, wE); }
-                else fetch_prev(i, wC);
-            }
-            // ---- the recursion; border pixels keep L = C (mgm_core.cc:953-960)
-            float L[LPL];
-            const bool border = (s == 0) || (i == 0) || (i == nI - 1);
-            {
-                const float mA = wA.m + P2, mB = wB.m + P2, mC = wC.m + P2, mE = wE.m + P2;
+            const bool borderA = (sA == 0) || (iA == 0) || (iA == nI - 1);
+            const bool borderB = (iB == 0) || (iB == nI - 1);
+            recurse(cA, inlineA, xB, xC, xE, borderA, LA);
+            recurse(cB, wAB, hNew, hC, hE, borderB, LB);
+            const float mAm = vec_min(LA), mBm = vec_min(LB);
+            if (actA) {
 #pragma unroll
-                for (int e = 0; e < LPL; e++) {
-                    float acc;
-                    if constexpr (TYPE == 0) {
-                        acc = nb_term<LPL>(wA, e, P1, mA);
-                        if (TSGM == 2) acc *= 0.5f;
-                        if (useCn) { float tt = nb_term<LPL>(wC, e, P1, mC); acc += (TSGM == 2) ? tt * 0.5f : tt; }
-                        if (useB)  { float tt = nb_term<LPL>(wB, e, P1, mB); acc += tt; }
-                        if (useE)  { float tt = nb_term<LPL>(wE, e, P1, mE); acc += tt; }
-                    } else {
-                        acc = nb_term<LPL>(wE, e, P1, mE);
-                        if (TSGM == 2) acc *= 0.5f;
-                        if (useB)  { float tt = nb_term<LPL>(wB, e, P1, mB); acc += (TSGM == 2) ? tt * 0.5f : tt; }
-                        if (useCn) { float tt = nb_term<LPL>(wC, e, P1, mC); acc += tt; }
-                        if (useA)  { float tt = nb_term<LPL>(wA, e, P1, mA); acc += tt; }
+                for (int e = 0; e < LPL; e++) hNew.v[e] = LA[e];
+                hNew.m = mAm;
+                fill_edges<LPL>(hNew, lane);
+                st_vec<LPL>(outA, LA);
+                outA += lstep;
+            }
+            if (actB) {
+#pragma unroll
+                for (int e = 0; e < LPL; e++) wAB.v[e] = LB[e];
+                wAB.m = mBm;
+                if (useA) fill_edges<LPL>(wAB, lane);
+                if (usePrev) st_vec<LPL>(myring + (iB & (kRing - 1)) * DP, LB);
+                st_vec<LPL>(outB, LB);
+                outB += lstep;
+                if (lane == 0 && usePrev) myringm[iB & (kRing - 1)] = mBm;
+                if (publish) {
+                    if (lane == 0) *lminB = mBm;
+                    lminB += strideI;
+                    if (((iB + 1) % kPublish) == 0 || iB == nI - 1) {
+                        __syncwarp();
+                        if (lane == 0) st_release(pd.progress + band, iB + 1);
                     }
-                    if constexpr (TSGM == 3) acc = div3_exact(acc);      // acc is finite and >= 0 on interior pixels
-                    if constexpr (TSGM == 4) acc = acc * 0.25f;
-                    L[e] = border ? c[e] : c[e] + acc;
                 }
-            }
-            // ---- minimum, LAST arg-minimum (mgm_core.cc:1015-1019)
-            float lm = L[0];
-#pragma unroll
-            for (int e = 1; e < LPL; e++) lm = fminf(lm, L[e]);
-            const float m = warp_min_f32(lm);
-            int am = -1;
-#pragma unroll
-            for (int e = 0; e < LPL; e++) if (L[e] == m) am = lane * LPL + e;
-            am = __reduce_max_sync(0xffffffffu, am);
-            // ---- hand over: registers (in-line), shared ring (next scanline of the band), HBM
-#pragma unroll
-            for (int e = 0; e < LPL; e++) wA.v[e] = L[e];
-            wA.m = m;
-            if (useA) fill_edges<LPL>(wA, lane);
-            if (usePrev) st_vec<LPL>(myring + (i & (kRing - 1)) * DP, L);
-            st_vec<LPL>(reinterpret_cast<float *>(l_out), L);
-            if (lane == 0) {
-                if (usePrev) myringm[i & (kRing - 1)] = m;
-                pd.Lmin[p_cur] = m;
-                pd.arg[p_cur] = (short)am;
-            }
-            l_out += lstep;
-            p_cur += strideI;
-            if (publish && (((i + 1) % kPublish) == 0 || i == nI - 1)) {
-                __syncwarp();
-                if (lane == 0) st_release(pd.progress + band, i + 1);
             }
         }
         __syncthreads();
     };
 
-    const int nsteps = nI + (kNW - 1) * SKEW;
     for (int t = 0; t < nsteps; t += U) {
-        if constexpr (U == 2) {          // window: C = newest, B = the one before
-            step(t, x1, x0, x2);
-            step(t + 1, x0, x1, x2);
-        } else {                         // window: E = newest, then C, then B
-            step(t, x1, x2, x0);
-            step(t + 1, x2, x0, x1);
-            step(t + 2, x0, x1, x2);
+        if constexpr (U == 2) {
+            step(t, x1, x0, x2, h0, h1, h2);
+            step(t + 1, x0, x1, x2, h1, h0, h2);
+        } else {
+            step(t, x1, x2, x0, h0, h1, h2);
+            step(t + 1, x2, x0, x1, h1, h2, h0);
+            step(t + 2, x0, x1, x2, h2, h0, h1);
         }
     }
     cp_async_wait<0>();
 }
 
 template <int LPL, int TSGM, bool SCALED>
-__global__ void __launch_bounds__(kNW * 32, (LPL <= 4) ? 2 : 1) aggregate_kernel(const __grid_constant__ AggParams P)
+__global__ void __launch_bounds__(kAggThreads) __maxnreg__((LPL <= 4) ? 128 : 255) aggregate_kernel(const __grid_constant__ AggParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_item;

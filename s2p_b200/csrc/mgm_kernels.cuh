@@ -112,7 +112,6 @@ __global__ void unpack_cost_kernel(const __half *__restrict__ C, size_t npix, in
 
 struct WtaParams {
     const float *L[kMaxPasses];
-    const short *arg[kMaxPasses];
     const __half *C;
     const short *lo, *hi;     // per-pixel label range (labels, not slots)
     const float *lut;
@@ -157,13 +156,24 @@ __global__ void wta_kernel(const WtaParams P)
     size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t p = warp; p < P.npix; p += nwarps) {
         float s[LPL];
+        int am[kMaxPasses];       // per pass: LAST slot attaining the pass minimum (mgm_core.cc:1015-1019)
 #pragma unroll
         for (int e = 0; e < LPL; e++) s[e] = 0.f;
-        for (int d = 0; d < P.ndir; d++) {
-            float v[LPL];
-            ld_vec_cg<LPL>(P.L[d] + p * DP + lane * LPL, v);
 #pragma unroll
-            for (int e = 0; e < LPL; e++) s[e] += v[e];
+        for (int d = 0; d < kMaxPasses; d++) {
+            am[d] = -1;
+            if (d < P.ndir) {
+                float v[LPL];
+                ld_vec_cg<LPL>(P.L[d] + p * DP + lane * LPL, v);
+                float lm = v[0];
+#pragma unroll
+                for (int e = 1; e < LPL; e++) lm = fminf(lm, v[e]);
+                const float md = warp_min_f32(lm);
+                int a = -1;
+#pragma unroll
+                for (int e = 0; e < LPL; e++) { if (v[e] == md) a = lane * LPL + e; s[e] += v[e]; }
+                am[d] = __reduce_max_sync(0xffffffffu, a);
+            }
         }
         HalfPack<LPL> cp = ld_cost<LPL>(P.C + p * DP + lane * LPL);
         float best = S2PB_INF;
@@ -176,14 +186,15 @@ __global__ void wta_kernel(const WtaParams P)
         }
         const float m = warp_min_f32(best);
         int cand = (best == m && bidx != 0x7fffffff) ? bidx : 0x7fffffff;
-        const int kbest = __reduce_min_sync(0xffffffffu, cand);   // first slot attaining the minimum
+        int kbest = __reduce_min_sync(0xffffffffu, cand);         // first slot attaining the minimum
+        if (kbest > DP - 1) kbest = 0;                            // unreachable: a pixel always has a finite S
         // every pixel has at least one finite S (its range always holds a finite cost)
         const int o = P.gmin + kbest;
         float minP = (float)o, minL = m;
 
         int confi = 0;
-        if (lane < P.ndir) confi = (P.arg[lane][p] == kbest) ? 1 : 0;
-        confi = __reduce_add_sync(0xffffffffu, confi);
+#pragma unroll
+        for (int d = 0; d < kMaxPasses; d++) confi += (am[d] == kbest) ? 1 : 0;
 
         if (P.S != nullptr || P.refine != 0) {
             __syncwarp();

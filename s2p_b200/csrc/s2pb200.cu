@@ -48,7 +48,6 @@ struct ViewWS {
     __half *C;
     float *L[kMaxPasses];
     float *Lmin[kMaxPasses];
-    short *arg[kMaxPasses];
     int *progress;         // [kMaxPasses][maxBands]
     float *disp, *cost, *conf, *tmp;
 };
@@ -109,7 +108,6 @@ static int slot_layout(Slot &s, int w, int h, int DP, int ndir, bool allocate)
         for (int p = 0; p < ndir; p++) {
             o = take(npix * DP * 4); if (allocate) v.L[p] = (float *)(b + o);
             o = take(npix * 4); if (allocate) v.Lmin[p] = (float *)(b + o);
-            o = take(npix * 2); if (allocate) v.arg[p] = (short *)(b + o);
         }
         o = take((size_t)kMaxPasses * mb * 4); if (allocate) v.progress = (int *)(b + o);
         o = take(npix * 4); if (allocate) v.disp = (float *)(b + o);
@@ -350,7 +348,7 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
         for (int p = 0; p < ndir; p++) {
             PassDesc &pd = P.pv[P.nPV++];
             fill_pass(pd, p, w, h);
-            pd.C = s.v[vi].C; pd.L = s.v[vi].L[p]; pd.Lmin = s.v[vi].Lmin[p]; pd.arg = s.v[vi].arg[p];
+            pd.C = s.v[vi].C; pd.L = s.v[vi].L[p]; pd.Lmin = s.v[vi].Lmin[p];
             pd.progress = s.v[vi].progress + (size_t)p * mb;
             if (pd.nBands > P.maxBands) P.maxBands = pd.nBands;
         }
@@ -402,7 +400,7 @@ static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t s
 static void fill_wta(WtaParams &P, const ViewWS &v, int ndir, int gmin, const s2pb_mgm_params *p, const float *lut, size_t npix)
 {
     memset(&P, 0, sizeof P);
-    for (int d = 0; d < ndir; d++) { P.L[d] = v.L[d]; P.arg[d] = v.arg[d]; }
+    for (int d = 0; d < ndir; d++) P.L[d] = v.L[d];
     P.C = v.C; P.lo = v.lo; P.hi = v.hi; P.lut = lut;
     P.ndir = ndir; P.gmin = gmin; P.fix_overcount = p->fix_overcount; P.refine = p->refine;
     P.inv_zoom_div = 1.f; P.npix = npix; P.S = nullptr; P.Dout = 0;
