@@ -1,0 +1,67 @@
+"""Single-band raster I/O for the drop-in boundary.
+
+The reference exchanges tile rasters as files: rectified images are
+float32 GeoTIFFs written through rasterio, the matcher binary writes plain float32 TIFFs with
+iio and ``plambda`` writes the mask as an 8-bit PNG.  rasterio is used when it is importable
+(as in a real s2p installation); otherwise Pillow / OpenCV read and write the same files.
+"""
+import numpy as np
+
+try:  # pragma: no cover - depends on the installation
+    import rasterio
+    _HAVE_RASTERIO = True
+except Exception:  # ImportError or a broken GDAL
+    rasterio = None
+    _HAVE_RASTERIO = False
+
+
+def read_band(path):
+    """-> 2-D float32 array (first band), NaN preserved."""
+    if _HAVE_RASTERIO:
+        with rasterio.open(path, "r") as f:
+            return np.ascontiguousarray(f.read(1).astype(np.float32))
+    try:
+        from PIL import Image
+        with Image.open(path) as im:
+            a = np.array(im)
+    except Exception:
+        import cv2
+        a = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        if a is None:
+            raise
+    if a.ndim == 3:
+        a = a[..., 0]
+    return np.ascontiguousarray(a.astype(np.float32))
+
+
+def image_size(path):
+    """-> (width, height)"""
+    if _HAVE_RASTERIO:
+        with rasterio.open(path, "r") as f:
+            return f.width, f.height
+    from PIL import Image
+    with Image.open(path) as im:
+        return im.size
+
+
+def write_float_tiff(path, a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if _HAVE_RASTERIO:
+        h, w = a.shape
+        with rasterio.open(path, "w", driver="GTiff", height=h, width=w, count=1, dtype="float32") as f:
+            f.write(a, 1)
+        return
+    from PIL import Image
+    Image.fromarray(a, mode="F").save(path, format="TIFF")
+
+
+def write_mask_png(path, m):
+    """uint8 0/1 mask, as plambda writes it (s2p/block_matching.py:32)."""
+    m = np.ascontiguousarray(m, dtype=np.uint8)
+    if _HAVE_RASTERIO:
+        h, w = m.shape
+        with rasterio.open(path, "w", driver="PNG", height=h, width=w, count=1, dtype="uint8") as f:
+            f.write(m, 1)
+        return
+    from PIL import Image
+    Image.fromarray(m, mode="L").save(path, format="PNG")

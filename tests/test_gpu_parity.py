@@ -128,3 +128,45 @@ def test_timeout_and_errors(engine):
     with pytest.raises(S2pbError) as e:
         engine.mgm(ref, sec, 5, 5, default_params("mgm"))
     assert e.value.code == _lib.ERR_ARG
+
+
+@pytest.mark.parametrize("name", ["plain", "wide", "nan_ref", "tsgm4_o4", "census3"])
+def test_against_reference_golden_vectors(engine, name):
+    """tests/golden/*.npz are outputs of the unmodified reference binary (tests/golden/make_golden.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as G
+    from s2p_b200.engine import default_params
+    ref, sec, dmin, dmax, kw = G.inputs(name)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm", **kw), want_right=True)
+    assert same(out["disp"], g["disp"]), "%d px differ from the reference" % nmismatch(out["disp"], g["disp"])
+    assert np.array_equal(out["conf"].astype(np.uint8), g["conf"])
+    if name != "nan_ref":      # see tests/test_oracle.py::test_identity_shift_equals_dct_shift_without_nodata
+        assert same(out["disp_right"], g["dispR"])
+
+
+def test_dropin_file_contract(engine, oracle, tmp_path):
+    """compute_disparity_map: same signature, files and exceptions as s2p/block_matching.py:35-336."""
+    import subprocess
+    from s2p_b200 import block_matching as bm, rasterio_compat as rio
+    h, w, dmin, dmax = 60, 100, -11, 12
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=42, nan_border=0.05)
+    im1, im2 = str(tmp_path / "rectified_ref.tif"), str(tmp_path / "rectified_sec.tif")
+    disp, mask = str(tmp_path / "rectified_disp.tif"), str(tmp_path / "rectified_mask.png")
+    rio.write_float_tiff(im1, ref)
+    rio.write_float_tiff(im2, sec)
+    assert bm.compute_disparity_map(im1, im2, disp, mask, "mgm", dmin + 0.4, dmax - 0.3) is None
+    d, c, _ = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params())
+    m = oracle.port.rejection_mask(d, ref, sec)
+    assert same(rio.read_band(disp), d)
+    assert same(rio.read_band(bm.confidence_path(disp)), c)
+    assert np.array_equal(rio.read_band(mask).astype(np.uint8), m)
+    with pytest.raises(bm.MaxDisparityRangeError):
+        bm.compute_disparity_map(im1, im2, disp, mask, "mgm", -100, 100, max_disp_range=10)
+    big_ref, big_sec, _ = make_pair(512, 512, -100, 100, seed=1)
+    rio.write_float_tiff(im1, big_ref)
+    rio.write_float_tiff(im2, big_sec)
+    with pytest.raises(subprocess.TimeoutExpired):      # tests/block_matching_test.py:18-21 in the reference
+        bm.compute_disparity_map(im1, im2, disp, mask, "mgm", -100, 100, timeout=0.001)

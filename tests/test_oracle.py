@@ -1,0 +1,88 @@
+"""CPU tests of the oracle (test infrastructure): the C restatement against the golden vectors
+(outputs of the unmodified reference binary) and, when oracle/_ref is present, against that binary
+run live.  Bit-exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import make_golden as G  # noqa: E402
+from util import nmismatch, same  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", sorted(G.CASES))
+def test_port_matches_golden(oracle, name):
+    ref, sec, dmin, dmax, kw = G.inputs(name)
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(dct_shift=1, **kw))
+    assert same(d, g["disp"]), "%d px differ" % nmismatch(d, g["disp"])
+    assert np.array_equal(c.astype(np.uint8), g["conf"])
+    assert same(dr, g["dispR"])
+
+
+@pytest.mark.parametrize("name", ["plain", "wide", "nan_ref", "tsgm4_o4", "census3"])
+def test_identity_shift_equals_dct_shift_without_nodata(oracle, name):
+    """The reference pushes the matched image of each view through a DCT round trip even for a zero
+    shift (mgm_costvolume.cc:23-60).  That is the identity except on exactly-zero pixels (NaN -> 0), whose
+    value then depends on the FFT library's rounding noise.  Without no-data pixels the product's identity
+    shift reproduces the reference bit for bit; with no-data in the reference image only, the right view
+    (which matches against the shifted reference image) may differ near the no-data area, while the
+    left disparity and the confidence of this fixture do not."""
+    ref, sec, dmin, dmax, kw = G.inputs(name)
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(dct_shift=0, **kw))
+    assert same(d, g["disp"]) and np.array_equal(c.astype(np.uint8), g["conf"])
+    if name != "nan_ref":
+        assert same(dr, g["dispR"])
+
+
+def _have_ref(oracle):
+    return oracle.have_ref()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(tsgm=1), dict(tsgm=2), dict(tsgm=4), dict(ndir=4), dict(ndir=2),
+                                dict(census_win=3), dict(census_win=7), dict(median=0, lr_mode=0, refine=0), dict(median=2)])
+def test_port_matches_reference_binary(oracle, kw):
+    if not _have_ref(oracle):
+        pytest.skip("oracle/_ref/mgm not built (needs /root/reference)")
+    from s2p_b200.synth import make_pair
+    h, w, dmin, dmax = 44, 72, -9, 10
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=33, nan_border=0.05)
+    P = oracle.mgm_params(dct_shift=1, **kw)
+    r = oracle.run_ref(ref, sec, dmin, dmax, P, threads=1)
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, P)
+    assert same(d, r["disp"]), "%d px differ" % nmismatch(d, r["disp"])
+    assert same(c, r["conf"]) and same(dr, r["dispR"])
+
+
+def test_port_cost_volume_matches_reference_dump(oracle):
+    if not _have_ref(oracle):
+        pytest.skip("oracle/_ref/mgm not built (needs /root/reference)")
+    from s2p_b200.synth import make_pair
+    h, w, dmin, dmax = 30, 64, -7, 9
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=7)
+    P = oracle.mgm_params(dct_shift=1, median=0, lr_mode=0, refine=0)
+    r = oracle.run_ref(ref, sec, dmin, dmax, P, extra_env={"DUMP_COSTVOLUME": "1"})
+    vol, dm = oracle.read_costvolume_dump(os.path.join(r["workdir"], "costvolume_left.dat"))
+    lo = np.full((h, w), dmin, np.int32)
+    hi = np.full((h, w), dmax, np.int32)
+    C = oracle.port.costvolume(ref, sec, lo, hi, dmin, dmax - dmin + 1, dct_shift=1)
+    assert dm == dmin and same(vol, C)
+
+
+def test_reference_sample_pair(oracle):
+    """The reference's own shipped rectified pair (279x271, two NaN pixels), read in place."""
+    src = "/root/reference/3rdparty/mgm_multi/matlab/data"
+    if not (_have_ref(oracle) and os.path.exists(os.path.join(src, "rectified_ref.tif"))):
+        pytest.skip("reference data not present")
+    from s2p_b200 import rasterio_compat as rio
+    a = rio.read_band(os.path.join(src, "rectified_ref.tif"))[:120, :160]
+    b = rio.read_band(os.path.join(src, "rectified_sec.tif"))[:120, :160]
+    P = oracle.mgm_params(dct_shift=1)
+    r = oracle.run_ref(a, b, -22, 19, P)
+    d, c, dr = oracle.port.mgm(a, b, -22, 19, P)
+    assert same(d, r["disp"]) and same(c, r["conf"]) and same(dr, r["dispR"])
