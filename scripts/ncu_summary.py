@@ -24,10 +24,11 @@ with open(out, "w") as f:
         for k in KEYS:
             if k in d:
                 f.write("%-90s %s %s\n" % (k, d[k], units[hdr.index(k)]))
-        try:
-            rd, wr = float(d["dram__bytes_read.sum"]), float(d["dram__bytes_write.sum"])
-            u = units[hdr.index("dram__bytes_read.sum")]
-            f.write("%-90s %.4f %s\n" % ("dram traffic (read+write)", rd + wr, u))
+        try:   # ncu prints one unit per COLUMN (first result's scale); values are already in that unit
+            sc = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd = float(d["dram__bytes_read.sum"]) * sc[units[hdr.index("dram__bytes_read.sum")]]
+            wr = float(d["dram__bytes_write.sum"]) * sc[units[hdr.index("dram__bytes_write.sum")]]
+            f.write("%-90s %.4f Gbyte\n" % ("dram traffic (read+write)", (rd + wr) / 1e9))
         except (KeyError, ValueError):
             pass
 print(open(out).read())
