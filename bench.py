@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--dmin", type=int, default=-64)
     ap.add_argument("--dmax", type=int, default=63)
     ap.add_argument("--slots", type=int, default=4, help="tiles in flight per GPU")
-    ap.add_argument("--cpu-procs", type=int, default=0, help="concurrent reference processes (0 = min(nproc, 32))")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="concurrent reference processes (0 = all host cores)")
     ap.add_argument("--cpu-rows", type=int, default=48, help="rows of the CPU sample strips")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -135,7 +135,7 @@ def make_strips(a, procs, base_tiles=None):
 
 def cpu_procs(a):
     n = os.cpu_count() or 1
-    return a.cpu_procs if a.cpu_procs > 0 else min(n, 32)
+    return a.cpu_procs if a.cpu_procs > 0 else n
 
 
 def run_reference(a, rank, world):

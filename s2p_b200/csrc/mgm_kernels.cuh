@@ -86,8 +86,25 @@ __global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__r
             }
         }
         __half *dst = C + p * DP + lane * LPL;
+        if constexpr (LPL % 2 == 0) {          // packed stores: 4, 8 or 16 bytes per lane
+            unsigned wds[LPL / 2];
 #pragma unroll
-        for (int e = 0; e < LPL; e++) dst[e] = __float2half_rn(c[e]);
+            for (int e = 0; e < LPL / 2; e++)
+                wds[e] = (unsigned)__half_as_ushort(__float2half_rn(c[2 * e])) | ((unsigned)__half_as_ushort(__float2half_rn(c[2 * e + 1])) << 16);
+            if constexpr (LPL % 8 == 0) {
+#pragma unroll
+                for (int q = 0; q < LPL / 8; q++) reinterpret_cast<uint4 *>(dst)[q] = make_uint4(wds[4 * q], wds[4 * q + 1], wds[4 * q + 2], wds[4 * q + 3]);
+            } else if constexpr (LPL % 4 == 0) {
+#pragma unroll
+                for (int q = 0; q < LPL / 4; q++) reinterpret_cast<uint2 *>(dst)[q] = make_uint2(wds[2 * q], wds[2 * q + 1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < LPL / 2; q++) reinterpret_cast<unsigned *>(dst)[q] = wds[q];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < LPL; e++) dst[e] = __float2half_rn(c[e]);
+        }
     }
 }
 
@@ -159,19 +176,22 @@ __global__ void wta_kernel(const WtaParams P)
         int am[kMaxPasses];       // per pass: LAST slot attaining the pass minimum (mgm_core.cc:1015-1019)
 #pragma unroll
         for (int e = 0; e < LPL; e++) s[e] = 0.f;
+        // all passes' vectors are requested before any is consumed (memory-level parallelism)
+        float v[kMaxPasses][LPL];
+#pragma unroll
+        for (int d = 0; d < kMaxPasses; d++)
+            if (d < P.ndir) ld_vec_cg<LPL>(P.L[d] + p * DP + lane * LPL, v[d]);
 #pragma unroll
         for (int d = 0; d < kMaxPasses; d++) {
             am[d] = -1;
             if (d < P.ndir) {
-                float v[LPL];
-                ld_vec_cg<LPL>(P.L[d] + p * DP + lane * LPL, v);
-                float lm = v[0];
+                float lm = v[d][0];
 #pragma unroll
-                for (int e = 1; e < LPL; e++) lm = fminf(lm, v[e]);
+                for (int e = 1; e < LPL; e++) lm = fminf(lm, v[d][e]);
                 const float md = warp_min_f32(lm);
                 int a = -1;
 #pragma unroll
-                for (int e = 0; e < LPL; e++) { if (v[e] == md) a = lane * LPL + e; s[e] += v[e]; }
+                for (int e = 0; e < LPL; e++) { if (v[d][e] == md) a = lane * LPL + e; s[e] += v[d][e]; }
                 am[d] = __reduce_max_sync(0xffffffffu, a);
             }
         }
