@@ -132,6 +132,8 @@ int s2pb_aggregate(s2pb_ctx *ctx, const float *C, const int32_t *lo, const int32
                    int fix_overcount, float *S, float *disp, float *cost, float *conf);
 /* img_tools.h:204-238 */
 int s2pb_median(s2pb_ctx *ctx, const float *in, float *out, int w, int h, int radius);
+/* remove_small_cc.c:9-73 with the intensity threshold 5 of mgm_multiscale.cc:332-333 */
+int s2pb_remove_small_cc(s2pb_ctx *ctx, const float *in, float *out, int w, int h, int minarea);
 /* s2p/block_matching.py:18-32 (plambda + backflow + plambda) */
 int s2pb_rejection_mask(s2pb_ctx *ctx, const float *disp, const float *im1, const float *im2,
                         int w, int h, uint8_t *mask);

@@ -532,6 +532,168 @@ int orc_mgm(const float *im1, const float *im2, int w, int h, int dmin, int dmax
     return 0;
 }
 
+/* ------------------------------------------------------------ `mgm_multi` */
+
+/* downsample2x, mgm_multiscale.cc:57-95: 10x10 Gaussian taps centred between pixels, weights
+ * renormalised over the in-image taps.  gcc contracts `acc += u*gg` into one fma at
+ * -O3 -march=native (checked in the disassembly of the reference object), so do we. */
+void orc_downsample2x(const float *u, int nx, int ny, float sigma, float *out)
+{
+    int onx = (nx + 1) / 2, ony = (ny + 1) / 2;
+    float g[100];
+    for (int j = 0; j < 10; j++)
+        for (int i = 0; i < 10; i++) {
+            float a = i - 4 - .5, b = j - 4 - .5;
+            double sq = a * a + b * b;
+            g[i + j * 10] = exp(-sq / (2.0 * sigma * sigma));
+        }
+#pragma omp parallel for
+    for (int j = 0; j < ony; j++)
+        for (int i = 0; i < onx; i++) {
+            float acc = 0, norm = 0;
+            for (int y = 0; y < 10; y++)
+                for (int x = 0; x < 10; x++) {
+                    int xx = i * 2 + x - 4, yy = j * 2 + y - 4;
+                    if (xx >= 0 && yy >= 0 && xx < nx && yy < ny) {
+                        float gg = g[x + y * 10];
+                        acc = fmaf(u[xx + yy * nx], gg, acc);
+                        norm += gg;
+                    }
+                }
+            out[i + j * onx] = acc / norm;
+        }
+}
+
+/* downsample2x_disp, mgm_multiscale.cc:98-117: 2x2 min (or max) pooling, halved */
+void orc_downsample2x_disp(const float *u, int nx, int ny, int is_max, float *out)
+{
+    int onx = (nx + 1) / 2;
+    for (int j = 0; j < ny; j += 2)
+        for (int i = 0; i < nx; i += 2) {
+            float vmin = INFINITY, vmax = -INFINITY;
+            for (int k = 0; k < 2; k++)
+                for (int l = 0; l < 2; l++) {
+                    int x = i + k, y = j + l;
+                    float t = (x < nx && y < ny) ? u[x + y * nx] : NAN;
+                    vmin = fminf(vmin, t);
+                    vmax = fmaxf(vmax, t);
+                }
+            out[i / 2 + j / 2 * onx] = is_max ? vmax / 2 : vmin / 2;
+        }
+}
+
+static inline float clampget(const float *a, int nx, int ny, int x, int y)
+{   /* valneumann, img_tools.h:77-85 */
+    if (x < 0) x = 0; if (x >= nx) x = nx - 1;
+    if (y < 0) y = 0; if (y >= ny) y = ny - 1;
+    return a[x + y * nx];
+}
+/* update_dmin_dmax, stereo_utils.cc:134-175.  (dminI, dmaxI) have disp's size; the fall-back images
+ * (dminP, dmaxP) may have another size: they are indexed with disp's coordinates, clamped to THEIR size
+ * (this is what happens when upsample2x_disp passes the fine-level images, mgm_multiscale.cc:43-44). */
+void orc_update_dmin_dmax(const float *disp, int nx, int ny, float *dminI, float *dmaxI,
+                          const float *dminP, const float *dmaxP, int pnx, int pny, int slack, int radius)
+{
+    float *tmin = malloc(sizeof(float) * nx * ny), *tmax = malloc(sizeof(float) * nx * ny);
+    memcpy(tmin, dminI, sizeof(float) * nx * ny);
+    memcpy(tmax, dmaxI, sizeof(float) * nx * ny);
+    if (slack < 0) slack = -slack;
+#pragma omp parallel for
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            float dmin = INFINITY, dmax = -INFINITY;
+            for (int dj = -radius; dj <= radius; dj++)
+                for (int di = -radius; di <= radius; di++) {
+                    float v = clampget(disp, nx, ny, i + di, j + dj);
+                    float vminP = clampget(dminP, pnx, pny, i + di, j + dj);
+                    float vmaxP = clampget(dmaxP, pnx, pny, i + di, j + dj);
+                    if (isfinite(v)) { dmin = fminf(dmin, v - slack); dmax = fmaxf(dmax, v + slack); }
+                    else { dmin = fminf(dmin, vminP); dmax = fmaxf(dmax, vmaxP); }
+                }
+            if (isfinite(dmin)) { tmin[i + j * nx] = dmin; tmax[i + j * nx] = dmax; }
+        }
+    memcpy(dminI, tmin, sizeof(float) * nx * ny);
+    memcpy(dmaxI, tmax, sizeof(float) * nx * ny);
+    free(tmin); free(tmax);
+}
+
+/* upsample2x_disp, mgm_multiscale.cc:36-48 (slack 8, radius 4, :33-34) + zoom_nn :16-31 */
+void orc_upsample2x_disp(const float *sdisp, int snx, int sny, float *dmin, float *dmax, int nx, int ny)
+{
+    int n = snx * sny;
+    float *d2 = malloc(sizeof(float) * n), *omin = calloc(n, sizeof(float)), *omax = calloc(n, sizeof(float));
+    for (int i = 0; i < n; i++) d2[i] = sdisp[i] * 2.0;
+    orc_update_dmin_dmax(d2, snx, sny, omin, omax, dmin, dmax, nx, ny, 8, 4);
+    for (int y = 0; y < ny; y++)
+        for (int x = 0; x < nx; x++) {
+            dmin[y * nx + x] = omin[(y / 2) * snx + x / 2];
+            dmax[y * nx + x] = omax[(y / 2) * snx + x / 2];
+        }
+    free(d2); free(omin); free(omax);
+}
+
+/* recursive_multiscale, mgm_multiscale.cc:339-410 */
+static void orc_recursive(const float *u, const float *v, int nx, int ny, float *dmin, float *dmax, float *dminR, float *dmaxR,
+                          const orc_params *P, int zoom, int numscales, int scale, float *dl, float *dr, float *confL)
+{
+    if (fmax(nx, ny) > 100 && fmin(nx, ny) > 50 && scale < numscales) {
+        int sx = (nx + 1) / 2, sy = (ny + 1) / 2, sn = sx * sy;
+        float *su = malloc(sizeof(float) * sn), *sv = malloc(sizeof(float) * sn);
+        float *a = malloc(sizeof(float) * sn), *b = malloc(sizeof(float) * sn), *c = malloc(sizeof(float) * sn), *d = malloc(sizeof(float) * sn);
+        float *sdl = malloc(sizeof(float) * sn), *sdr = malloc(sizeof(float) * sn), *sconf = malloc(sizeof(float) * sn);
+        orc_downsample2x(u, nx, ny, 0.8f, su);
+        orc_downsample2x(v, nx, ny, 0.8f, sv);
+        orc_downsample2x_disp(dmin, nx, ny, 0, a);
+        orc_downsample2x_disp(dmax, nx, ny, 1, b);
+        orc_downsample2x_disp(dminR, nx, ny, 0, c);
+        orc_downsample2x_disp(dmaxR, nx, ny, 1, d);
+        orc_recursive(su, sv, sx, sy, a, b, c, d, P, zoom, numscales, scale + 1, sdl, sdr, sconf);
+        orc_upsample2x_disp(sdl, sx, sy, dmin, dmax, nx, ny);
+        orc_upsample2x_disp(sdr, sx, sy, dminR, dmaxR, nx, ny);
+        free(su); free(sv); free(a); free(b); free(c); free(d); free(sdl); free(sdr); free(sconf);
+    }
+    orc_mgm_call(u, v, nx, ny, dmin, dmax, dminR, dmaxR, P, zoom, dl, dr, confL);
+}
+
+/* main() of mgm_multi (main_mgm_multi.cc:88-256), memory to memory.  The confidence written by
+ * -confidence_consensusL is the one of the full-resolution ZOOM=1 call (the outer `param`, :197-209). */
+int orc_mgm_multi(const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+                  const orc_params *P, float *disp, float *conf, float *dispR)
+{
+    int npix = w * h;
+    float *u = malloc(sizeof(float) * npix), *v = malloc(sizeof(float) * npix);
+    float *a = malloc(sizeof(float) * npix), *b = malloc(sizeof(float) * npix);
+    float *c = malloc(sizeof(float) * npix), *d = malloc(sizeof(float) * npix);
+    float *dr = malloc(sizeof(float) * npix), *conf2 = malloc(sizeof(float) * npix);
+    for (int i = 0; i < npix; i++) {
+        u[i] = isfinite(im1[i]) ? im1[i] : 0;
+        v[i] = isfinite(im2[i]) ? im2[i] : 0;
+        a[i] = dmin; b[i] = dmax; c[i] = -dmax; d[i] = -dmin;
+        if (isnan(im1[i])) { a[i] = dmin; b[i] = dmin + 1; }
+        if (isnan(im2[i])) { c[i] = dmin; d[i] = dmin + 1; }
+    }
+    orc_recursive(u, v, w, h, a, b, c, d, P, 1, P->scales, 0, disp, dr, conf);
+    if (P->subpix > 1) {                                       /* :203-209 */
+        orc_update_dmin_dmax(disp, w, h, a, b, a, b, w, h, 2, 4);
+        orc_update_dmin_dmax(dr, w, h, c, d, c, d, w, h, 2, 4);
+        orc_recursive(u, v, w, h, a, b, c, d, P, P->subpix, 0, 0, disp, dr, conf2);
+    }
+    if (P->lr_mode == 2) {                                     /* :212-217 */
+        float *tl = malloc(sizeof(float) * npix), *tr = malloc(sizeof(float) * npix);
+        memcpy(tl, disp, sizeof(float) * npix); memcpy(tr, dr, sizeof(float) * npix);
+        orc_lrcheck(dr, w, h, tl, w, P->lr_tau);
+        orc_lrcheck(disp, w, h, tr, w, P->lr_tau);
+        free(tl); free(tr);
+    }
+    for (int i = 0; i < npix; i++) {
+        if (isnan(im1[i])) disp[i] = NAN;
+        if (isnan(im2[i])) dr[i] = NAN;
+    }
+    if (dispR) memcpy(dispR, dr, sizeof(float) * npix);
+    free(u); free(v); free(a); free(b); free(c); free(d); free(dr); free(conf2);
+    return 0;
+}
+
 /* ----------------------------------------------------- rejection mask (a10) */
 
 static float cubic1(const float v[4], float x)

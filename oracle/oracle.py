@@ -129,12 +129,33 @@ class port:
         return disp, conf, dispR
 
     @staticmethod
+    def mgm_multi(im1, im2, dmin, dmax, params=None):
+        """-> disp (left), conf, dispR : the `mgm_multi` binary from memory to memory."""
+        params = params or mgm_multi_params()
+        im1, im2 = _f32(im1), _f32(im2)
+        h, w = im1.shape
+        disp = np.empty((h, w), np.float32)
+        conf = np.empty((h, w), np.float32)
+        dispR = np.empty((h, w), np.float32)
+        lib().orc_mgm_multi(_p(im1), _p(im2), w, h, int(dmin), int(dmax), ctypes.byref(params),
+                            _p(disp), _p(conf), _p(dispR))
+        return disp, conf, dispR
+
+    @staticmethod
     def rejection_mask(disp, im1, im2):
         disp, im1, im2 = _f32(disp), _f32(im1), _f32(im2)
         h, w = disp.shape
         mask = np.empty((h, w), np.uint8)
         lib().orc_rejection_mask(_p(disp), _p(im1), _p(im2), w, h, _p(mask, ctypes.c_uint8))
         return mask
+
+    @staticmethod
+    def remove_small_cc(img, minarea=25, thr=5.0):
+        img = _f32(img)
+        h, w = img.shape
+        out = np.empty_like(img)
+        lib().orc_remove_small_cc(w, h, _p(img), _p(out), int(minarea), ctypes.c_float(thr))
+        return out
 
     @staticmethod
     def median(img, radius=1):

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "s2pb_aggregate": (c_int, [c_void_p, _f, POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int, c_int, c_float, c_float,
                                c_int, c_int, c_int, _f, _f, _f, _f]),
     "s2pb_median": (c_int, [c_void_p, _f, _f, c_int, c_int, c_int]),
+    "s2pb_remove_small_cc": (c_int, [c_void_p, _f, _f, c_int, c_int, c_int]),
     "s2pb_rejection_mask": (c_int, [c_void_p, _f, _f, _f, c_int, c_int, POINTER(c_uint8)]),
     "s2pb_last_timings": (c_int, [c_void_p, c_int, _f]),
     "s2pb_kernel_launches": (c_longlong, [c_void_p]),

@@ -53,8 +53,11 @@ __global__ void has_nan_kernel(const float *__restrict__ in, int n, int *flag)
 // One warp per pixel.  mgm_costvolume.cc:140-172: label o of pixel (x,y) compares census
 // codes cu(x,y) and cv(x+o,y); +INF when x+o is outside; if no label of the pixel's range is
 // finite, the whole range is set to 0.  Slots outside [lo,hi] stay +INF.
+// With ZOOMFACTOR = 2 (mgm_costvolume.cc:145-154) label o compares cu(x) with the census of the matched image
+// shifted by (o mod 2)/2 pixel, at column x + floor(o/2): cv = shift 0, cv1 = shift 1/2.
 template <int LPL>
-__global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__restrict__ cv, int w, int h,
+__global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__restrict__ cv, const uint64_t *__restrict__ cv1,
+                            int zoom, int w, int h,
                             const short *__restrict__ lo, const short *__restrict__ hi, int gmin, __half *__restrict__ C)
 {
     constexpr int DP = 32 * LPL;
@@ -74,7 +77,9 @@ __global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__r
             float v = S2PB_INF;
             if (o >= l && o <= hgh) {
                 int q = x + o;
-                if (q >= 0 && q < w) { v = (float)__popcll(a ^ cv[row + q]); anyfinite = true; }
+                const uint64_t *codes = cv;
+                if (zoom == 2) { q = x + (o >> 1); if (o & 1) codes = cv1; }      // floor(o/2), goodmod(o,2)
+                if (q >= 0 && q < w) { v = (float)__popcll(a ^ codes[row + q]); anyfinite = true; }
             }
             c[e] = v;
         }

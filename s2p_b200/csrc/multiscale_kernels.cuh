@@ -1,0 +1,202 @@
+// multiscale_kernels.cuh -- the extra stages of `mgm_multi`.
+//
+// Behavioural reference, paths under /root/reference/3rdparty/mgm_multi: mgm_multiscale.cc:16-117
+// (zoom_nn, upsample2x_disp, downsample2x, downsample2x_disp), stereo_utils.cc:134-175
+// (update_dmin_dmax), remove_small_cc.c:9-73, shear.c:28-101 + mgm_costvolume.cc:23-60 (DCT shift).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace s2pb {
+
+// downsample2x (mgm_multiscale.cc:57-95): 10x10 Gaussian taps centred between pixels (CX = 4),
+// renormalised over the in-image taps; y outer / x inner accumulation, `acc += u*g` contracted to one
+// fma exactly as gcc does for the reference at -O3 -march=native.
+struct GaussTaps { float g[100]; };
+__global__ void downsample2x_kernel(const float *__restrict__ u, int nx, int ny, GaussTaps T, float *__restrict__ out, int onx, int ony)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= onx || j >= ony) return;
+    float acc = 0.f, norm = 0.f;
+    for (int y = 0; y < 10; y++) {
+        int yy = j * 2 + y - 4;
+        for (int x = 0; x < 10; x++) {
+            int xx = i * 2 + x - 4;
+            if (xx >= 0 && yy >= 0 && xx < nx && yy < ny) {
+                float gg = T.g[x + y * 10];
+                acc = fmaf(u[(size_t)yy * nx + xx], gg, acc);
+                norm += gg;
+            }
+        }
+    }
+    out[(size_t)j * onx + i] = __fdiv_rn(acc, norm);
+}
+
+// downsample2x_disp (mgm_multiscale.cc:98-117): 2x2 min / max pooling of the range images, halved
+__global__ void downsample2x_disp_kernel(const float *__restrict__ u, int nx, int ny, int is_max, float *__restrict__ out, int onx, int ony)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= onx || j >= ony) return;
+    float vmin = __int_as_float(0x7f800000), vmax = __int_as_float(0xff800000);
+    for (int k = 0; k < 2; k++)
+        for (int l = 0; l < 2; l++) {
+            int x = 2 * i + k, y = 2 * j + l;
+            if (x < nx && y < ny) { float t = u[(size_t)y * nx + x]; vmin = fminf(vmin, t); vmax = fmaxf(vmax, t); }
+        }
+    out[(size_t)j * onx + i] = (is_max ? vmax : vmin) * 0.5f;
+}
+
+// update_dmin_dmax (stereo_utils.cc:134-175).  disp, dminI/dmaxI (in) and omin/omax (out) are nx x ny;
+// the fall-back images dminP/dmaxP are pnx x pny and are read at disp's coordinates clamped to THEIR size.
+__global__ void update_ranges_kernel(const float *__restrict__ disp, float scale, int nx, int ny, const float *__restrict__ dminI,
+                                     const float *__restrict__ dmaxI, const float *__restrict__ dminP, const float *__restrict__ dmaxP,
+                                     int pnx, int pny, float slack, int radius, float *__restrict__ omin, float *__restrict__ omax)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= nx || j >= ny) return;
+    float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
+    for (int dj = -radius; dj <= radius; dj++)
+        for (int di = -radius; di <= radius; di++) {
+            int x = min(max(i + di, 0), nx - 1), y = min(max(j + dj, 0), ny - 1);
+            float v = disp[(size_t)y * nx + x] * scale;         // upsample2x_disp doubles the coarse disparity first
+            if (isfinite(v)) { dmin = fminf(dmin, v - slack); dmax = fmaxf(dmax, v + slack); }
+            else {
+                int px = min(max(i + di, 0), pnx - 1), py = min(max(j + dj, 0), pny - 1);
+                dmin = fminf(dmin, dminP[(size_t)py * pnx + px]);
+                dmax = fmaxf(dmax, dmaxP[(size_t)py * pnx + px]);
+            }
+        }
+    size_t o = (size_t)j * nx + i;
+    if (isfinite(dmin)) { omin[o] = dmin; omax[o] = dmax; }
+    else { omin[o] = dminI ? dminI[o] : 0.f; omax[o] = dmaxI ? dmaxI[o] : 0.f; }
+}
+
+// zoom_nn by 2 (mgm_multiscale.cc:16-31)
+__global__ void zoom2_kernel(const float *__restrict__ in, int inx, float *__restrict__ out, int nx, int ny)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    out[(size_t)y * nx + x] = in[(size_t)(y / 2) * inx + x / 2];
+}
+
+// first-level range images of one view (main_mgm_multi.cc:160-196)
+__global__ void init_ranges_kernel(const float *__restrict__ img, int n, float lo_all, float hi_all, float sentinel,
+                                   float *__restrict__ clean, float *__restrict__ dmin, float *__restrict__ dmax)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = img[i];
+    bool isn = isnan(v);
+    clean[i] = isfinite(v) ? v : 0.f;
+    dmin[i] = isn ? sentinel : lo_all;
+    dmax[i] = isn ? sentinel + 1.f : hi_all;
+}
+
+// float range images -> integer label ranges of one mgm_call (allocate_costvolume, mgm_costvolume.cc:63-72,
+// after the scaling by ZOOMFACTOR of mgm_multiscale.cc:218-219) and their hull (hull[0] = min lo, hull[1] = max hi)
+__global__ void label_ranges_kernel(const float *__restrict__ dmin, const float *__restrict__ dmax, int n, float zoom,
+                                    short *__restrict__ lo, short *__restrict__ hi, int *hull)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int l = 0x7fffffff, h = (int)0x80000000;
+    if (i < n) {
+        l = (int)floorf(dmin[i] * zoom);
+        h = (int)ceilf(dmax[i] * zoom);
+        lo[i] = (short)l; hi[i] = (short)h;
+    }
+    l = __reduce_min_sync(0xffffffffu, l);
+    h = __reduce_max_sync(0xffffffffu, h);
+    if ((threadIdx.x & 31) == 0) { atomicMin(hull, l); atomicMax(hull + 1, h); }
+}
+
+// ---- remove_small_cc (remove_small_cc.c:9-73): union-find over the 4-neighbour links the reference makes
+// (only from pixels with i < w-1 and j < h-1; |difference| < threshold; NaN never joins), then every
+// component with area <= minarea becomes NaN.  Any union-find yields the same partition.
+__device__ __forceinline__ int uf_find(const int *lab, int a)
+{   // read-only chase: parents only ever move towards smaller roots, so this terminates under concurrent unions
+    while (true) { int p = ((const volatile int *)lab)[a]; if (p == a) return a; a = p; }
+}
+__device__ __forceinline__ void uf_union(int *lab, int a, int b)
+{
+    while (true) {
+        a = uf_find(lab, a); b = uf_find(lab, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }                            // a > b: hang the larger root below the smaller
+        int old = atomicCAS(lab + a, a, b);
+        if (old == a) return;
+    }
+}
+__global__ void cc_init_kernel(const float *__restrict__ in, int n, int *__restrict__ lab, int *__restrict__ area)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { lab[i] = isnan(in[i]) ? -1 : i; area[i] = 0; }
+}
+__global__ void cc_link_kernel(const float *__restrict__ in, int w, int h, float thr, int *lab)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= w - 1 || j >= h - 1) return;
+    int p0 = j * w + i;
+    if (lab[p0] < 0) return;
+    float a = in[p0];
+    int p1 = p0 + 1, p2 = p0 + w;
+    if (lab[p1] >= 0 && fabs((double)(a - in[p1])) < (double)thr) uf_union(lab, p0, p1);
+    if (lab[p2] >= 0 && fabs((double)(a - in[p2])) < (double)thr) uf_union(lab, p0, p2);
+}
+__global__ void cc_area_kernel(int n, int *lab, int *area)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && lab[i] >= 0) atomicAdd(area + uf_find(lab, i), 1);
+}
+__global__ void cc_filter_kernel(const float *__restrict__ in, int n, const int *__restrict__ lab, const int *__restrict__ area,
+                                 int minarea, float *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = lab[i];
+    if (r >= 0) r = uf_find(lab, i);
+    out[i] = (r >= 0 && area[r] <= minarea) ? __int_as_float(0x7fc00000) : in[i];
+}
+
+// ---- sub-pixel row shift out(x) = in(x + q) through the DCT interpolant, double precision
+// (shear.c:28-101 with shear = 0, called by shift() with translation -q, mgm_costvolume.cc:23-43).
+// One block per row: dct[k] = (2/n) sum_j x_j cos(pi (j+1/2) k / n), then
+// out[i] = dct[0]/2 + sum_{k>=1} dct[k] cos(pi k (i + 1/2 + q) / n), evaluated as the reference's
+// sym/antisym pair 0.5*(REDFT01(dct*cos(ka)) + RODFT01(dct*sin(ka))), a = -pi q / n.
+__global__ void dct_shift_kernel(const float *__restrict__ in, float *__restrict__ out, int n, float q)
+{
+    extern __shared__ double sm[];
+    double *x = sm, *dct = sm + n, *tab = sm + 2 * n;           // tab[m] = cos(pi m / (2n)), m in [0, 4n); 7n doubles in all
+    const int row = blockIdx.x;
+    for (int m = threadIdx.x; m < 4 * n; m += blockDim.x) tab[m] = cospi((double)m / (double)(2 * n));
+    for (int j = threadIdx.x; j < n; j += blockDim.x) x[j] = (double)in[(size_t)row * n + j];
+    __syncthreads();
+    const int four_n = 4 * n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double acc = 0.0;
+        int idx = k % four_n, stepi = (2 * k) % four_n;          // (2j+1)k mod 4n
+        for (int j = 0; j < n; j++) {
+            acc += 2.0 * x[j] * tab[idx];
+            idx += stepi; if (idx >= four_n) idx -= four_n;
+        }
+        dct[k] = acc / n;
+    }
+    __syncthreads();
+    const double t = (double)(-q);                               // translation passed by shift(): (0., -q) as floats
+    const double a = (3.14159265358979323846 / n) * t;
+    double *ck = x, *sk = sm + 6 * n;                            // x is dead: reuse it for dct[k] cos(ka); sk = dct[k] sin(ka)
+    for (int k = threadIdx.x; k < n; k += blockDim.x) { ck[k] = dct[k] * cos(k * a); sk[k] = dct[k] * sin(k * a); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double sym = ck[0], anti = 0.0;
+        int idx = 0; const int stepi = (2 * i + 1) % four_n;     // k(2i+1) mod 4n ; sin(theta) = cos(theta - pi/2) -> idx - n
+        for (int k = 1; k < n; k++) {
+            idx += stepi; if (idx >= four_n) idx -= four_n;
+            int sidx = idx - n; if (sidx < 0) sidx += four_n;
+            sym += 2.0 * ck[k] * tab[idx];
+            anti += 2.0 * sk[k] * tab[sidx];
+        }
+        out[(size_t)row * n + i] = (float)(0.5 * (sym + anti));
+    }
+}
+
+}  // namespace s2pb

@@ -6,6 +6,7 @@
 // (s2p/block_matching.py:18-32).  There is no CPU fallback in this file.
 #include "../../include/s2pb200.h"
 #include "mgm_kernels.cuh"
+#include "multiscale_kernels.cuh"
 #include "agg_dispatch.h"
 
 #include <chrono>
@@ -13,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <thread>
 #include <vector>
@@ -62,10 +64,15 @@ struct Slot {
     float *d_in[2] = {nullptr, nullptr};
     float *d_disp = nullptr, *d_conf = nullptr, *d_dispR = nullptr;
     uint8_t *d_mask = nullptr;
+    char *io_base = nullptr;
+    size_t io_pix = 0;
     float *h_in[2] = {nullptr, nullptr};          // pinned
     float *h_disp = nullptr, *h_conf = nullptr, *h_dispR = nullptr;
     uint8_t *h_mask = nullptr;
     size_t h_pix = 0;
+    // bump arena for the pyramid of mgm_multi (images, range images, per-level results)
+    char *arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[S2PB_T_COUNT + 1] = {};
     cudaEvent_t done = nullptr;
@@ -77,6 +84,7 @@ struct s2pb_ctx {
     std::vector<Slot> slots;
     int *abort_flag = nullptr;     // pinned + mapped: the host raises it on timeout
     int *scratch_flag = nullptr;   // pinned + mapped: device -> host one-word answers
+    int *d_scratch = nullptr;      // 64 words of device memory (hull accumulators of mgm_multi)
     long long launches = 0;
 };
 
@@ -118,18 +126,28 @@ static int slot_layout(Slot &s, int w, int h, int DP, int ndir, bool allocate)
     size_t o;
     o = take(256); if (allocate) s.next_item = (int *)(b + o);
     o = take(256); if (allocate) s.lut = (float *)(b + o);
-    for (int i = 0; i < 2; i++) { o = take(npix * 4); if (allocate) s.d_in[i] = (float *)(b + o); }
-    o = take(npix * 4); if (allocate) s.d_disp = (float *)(b + o);
-    o = take(npix * 4); if (allocate) s.d_conf = (float *)(b + o);
-    o = take(npix * 4); if (allocate) s.d_dispR = (float *)(b + o);
-    o = take(npix); if (allocate) s.d_mask = (uint8_t *)(b + o);
     if (!allocate) s.bytes = off;
     return 0;
 }
 
+// device-side staging of the host-buffer API (inputs, outputs); separate from the workspace because
+// mgm_multi re-carves the workspace at every pyramid level
+static int slot_io_ensure(Slot &s, size_t npix)
+{
+    if (s.io_pix >= npix) return S2PB_OK;
+    if (s.io_base) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.io_base)); s.io_base = nullptr; s.io_pix = 0; }
+    size_t stride = align_up(npix * 4, 256);
+    cudaError_t e = cudaMalloc((void **)&s.io_base, stride * 6);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(S2PB_ERR_NOMEM, "I/O staging of %zu bytes: %s", stride * 6, cudaGetErrorString(e)); }
+    s.d_in[0] = (float *)s.io_base; s.d_in[1] = (float *)(s.io_base + stride);
+    s.d_disp = (float *)(s.io_base + 2 * stride); s.d_conf = (float *)(s.io_base + 3 * stride);
+    s.d_dispR = (float *)(s.io_base + 4 * stride); s.d_mask = (uint8_t *)(s.io_base + 5 * stride);
+    s.io_pix = npix;
+    return S2PB_OK;
+}
+
 static int slot_ensure(s2pb_ctx *ctx, Slot &s, int w, int h, int DP, int ndir)
 {
-    if (s.base && s.w == w && s.h == h && s.DP == DP && s.ndir >= ndir) return S2PB_OK;
     Slot probe;
     slot_layout(probe, w, h, DP, ndir, false);
     if (!s.base || probe.bytes > s.bytes) {
@@ -142,8 +160,6 @@ static int slot_ensure(s2pb_ctx *ctx, Slot &s, int w, int h, int DP, int ndir)
                         probe.bytes / 1073741824.0, w, h, DP, cudaGetErrorString(e));
         }
         s.bytes = probe.bytes;
-    } else {
-        CK(cudaStreamSynchronize(s.stream));
     }
     s.w = w; s.h = h; s.DP = DP; s.ndir = ndir;
     size_t keep = s.bytes;
@@ -204,11 +220,13 @@ extern "C" s2pb_ctx *s2pb_create(int device)
     s2pb_ctx *ctx = new s2pb_ctx;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaHostAlloc((void **)&ctx->abort_flag, 2 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&ctx->abort_flag, 16 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
         fail(S2PB_ERR_CUDA, "cudaHostAlloc failed"); delete ctx; return nullptr;
     }
-    ctx->scratch_flag = ctx->abort_flag + 1;
-    ctx->abort_flag[0] = ctx->abort_flag[1] = 0;
+    ctx->scratch_flag = ctx->abort_flag + 8;
+    for (int i = 0; i < 16; i++) ctx->abort_flag[i] = 0;
+    cudaFuncSetAttribute(dct_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (cudaMalloc((void **)&ctx->d_scratch, 256) != cudaSuccess) { fail(S2PB_ERR_CUDA, "cudaMalloc failed"); delete ctx; return nullptr; }
     ctx->slots.resize(1);
     if (slot_init(ctx, ctx->slots[0]) != S2PB_OK) { delete ctx; return nullptr; }
     if (agg_configure() != 0) { fail(S2PB_ERR_CUDA, "cudaFuncSetAttribute failed for the aggregation kernels"); delete ctx; return nullptr; }
@@ -222,12 +240,15 @@ extern "C" void s2pb_destroy(s2pb_ctx *ctx)
     for (auto &s : ctx->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.base) cudaFree(s.base);
+        if (s.arena) cudaFree(s.arena);
+        if (s.io_base) cudaFree(s.io_base);
         if (s.h_in[0]) cudaFreeHost(s.h_in[0]);
         for (auto &e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (ctx->abort_flag) cudaFreeHost(ctx->abort_flag);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     delete ctx;
 }
 
@@ -280,11 +301,13 @@ static int check_params(const s2pb_mgm_params *p, int w, int h, int dmin, int dm
     if (p->census_win != 3 && p->census_win != 5 && p->census_win != 7) return fail(S2PB_ERR_ARG, "census_win must be 3, 5 or 7");
     if (p->median < 0 || p->median > 2) return fail(S2PB_ERR_ARG, "median radius must be 0..2");
     if (p->refine < 0 || p->refine > 2) return fail(S2PB_ERR_ARG, "refine must be 0 (none), 1 (vfit) or 2 (parabola)");
-    if (p->scales >= 0 || p->subpix > 1)
-        return fail(S2PB_ERR_UNSUPPORTED, "mgm_multi (multiscale / SUBPIX=2) is not implemented in this build");
-    if (p->remove_small_cc > 0) return fail(S2PB_ERR_UNSUPPORTED, "REMOVESMALLCC is not implemented in this build");
+    if (p->subpix != 1 && p->subpix != 2) return fail(S2PB_ERR_UNSUPPORTED, "SUBPIX must be 1 or 2");
+    if (p->scales < 0 && p->subpix != 1) return fail(S2PB_ERR_ARG, "SUBPIX=2 only exists in mgm_multi (scales >= 0)");
+    if (p->scales < 0 && p->remove_small_cc > 0) return fail(S2PB_ERR_UNSUPPORTED, "REMOVESMALLCC is only wired into the mgm_multi path");
     if (p->mindiff >= 0) return fail(S2PB_ERR_UNSUPPORTED, "MINDIFF is not implemented in this build");
-    if (p->lr_mode != 0 && p->lr_mode != 1) return fail(S2PB_ERR_UNSUPPORTED, "TESTLRRL=2 only exists in mgm_multi");
+    if (p->lr_mode < 0 || p->lr_mode > 2) return fail(S2PB_ERR_ARG, "TESTLRRL must be 0, 1 or 2");
+    if (p->scales < 0 && p->lr_mode == 2) return fail(S2PB_ERR_ARG, "TESTLRRL=2 only exists in mgm_multi");
+    if (p->scales >= 0 && w > 4000) return fail(S2PB_ERR_UNSUPPORTED, "mgm_multi tiles wider than 4000 px are not supported");
     if (abs(dmin) > 16000 || abs(dmax) > 16000) return fail(S2PB_ERR_ARG, "disparity bounds out of the int16 label range");
     return S2PB_OK;
 }
@@ -362,10 +385,10 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
     return S2PB_OK;
 }
 
-template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t *cv, int w, int h, const short *lo, const short *hi,
-                                             int gmin, __half *C, int sm, cudaStream_t st)
+template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t *cv, const uint64_t *cv1, int zoom, int w, int h,
+                                             const short *lo, const short *hi, int gmin, __half *C, int sm, cudaStream_t st)
 {
-    cost_kernel<LPL><<<sm * 8, 256, 0, st>>>(cu, cv, w, h, lo, hi, gmin, C);
+    cost_kernel<LPL><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, zoom, w, h, lo, hi, gmin, C);
 }
 template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStream_t st)
 {
@@ -382,9 +405,9 @@ template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStre
     }
 
 static int launch_cost(s2pb_ctx *ctx, int LPL, const uint64_t *cu, const uint64_t *cv, int w, int h, const short *lo, const short *hi,
-                       int gmin, __half *C, cudaStream_t st)
+                       int gmin, __half *C, cudaStream_t st, const uint64_t *cv1 = nullptr, int zoom = 1)
 {
-    LPL_SWITCH(LPL, launch_cost_t<K>(cu, cv, w, h, lo, hi, gmin, C, ctx->sm_count, st));
+    LPL_SWITCH(LPL, launch_cost_t<K>(cu, cv, cv1, zoom, w, h, lo, hi, gmin, C, ctx->sm_count, st));
     CK(cudaGetLastError());
     ctx->launches++;
     return S2PB_OK;
@@ -407,12 +430,277 @@ static void fill_wta(WtaParams &P, const ViewWS &v, int ndir, int gmin, const s2
     P.disp = v.disp; P.cost = v.cost; P.conf = v.conf;
 }
 
+// ------------------------------------------------------------------ mgm_multi (device level)
+
+static int arena_reset(Slot &s, size_t need)
+{
+    if (need > s.arena_cap) {
+        if (s.arena) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.arena)); s.arena = nullptr; s.arena_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&s.arena, need);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(S2PB_ERR_NOMEM, "pyramid arena of %zu bytes: %s", need, cudaGetErrorString(e)); }
+        s.arena_cap = need;
+    }
+    s.arena_off = 0;
+    return S2PB_OK;
+}
+template <class T> static T *arena_take(Slot &s, size_t n)
+{
+    size_t o = s.arena_off;
+    s.arena_off = align_up(o + n * sizeof(T), 256);
+    return s.arena_off <= s.arena_cap ? (T *)(s.arena + o) : nullptr;
+}
+
+struct Level {
+    int w, h;
+    float *u, *v;                          // NaN-free images
+    float *dminL, *dmaxL, *dminR, *dmaxR;  // per-pixel disparity bounds (pixels, float)
+    float *dl, *dr, *conf;                 // results of this level's mgm_call
+};
+
+static GaussTaps gauss_taps(float sigma)
+{   // mgm_multiscale.cc:66-71
+    GaussTaps T;
+    for (int j = 0; j < 10; j++)
+        for (int i = 0; i < 10; i++) {
+            float a = i - 4 - .5, b = j - 4 - .5;
+            double sq = a * a + b * b;
+            T.g[i + j * 10] = (float)exp(-sq / (2.0 * sigma * sigma));
+        }
+    return T;
+}
+
+// remove_small_cc on a device image (in -> out), scratch: two int images
+static int launch_remove_small_cc(s2pb_ctx *ctx, const float *in, float *out, int w, int h, int minarea, int *lab, int *area, cudaStream_t st)
+{
+    int n = w * h;
+    dim3 b2(32, 8);
+    cc_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(in, n, lab, area);
+    cc_link_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(in, w, h, 5.f, lab);
+    cc_area_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, lab, area);
+    cc_filter_kernel<<<(n + 255) / 256, 256, 0, st>>>(in, n, lab, area, minarea, out);
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    return S2PB_OK;
+}
+
+// S2PB_TRACE=1: synchronise and report after every stage of mgm_multi; 2: report only (debugging aid)
+static int trace_mode() { static int t = -1; if (t < 0) { const char *e = getenv("S2PB_TRACE"); t = e ? atoi(e) : 0; } return t; }
+#define TRACE(st, ...) do { if (trace_mode()) { cudaError_t e_ = trace_mode() == 1 ? cudaStreamSynchronize(st) : cudaSuccess; \
+    fprintf(stderr, "[s2pb] " __VA_ARGS__); fprintf(stderr, " -> %s\n", cudaGetErrorString(e_)); fflush(stderr); } } while (0)
+
+// One mgm_call (mgm_multiscale.cc:161-335) on device images with per-pixel bounds.
+static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb_mgm_params *p, cudaStream_t st)
+{
+    const int w = L.w, h = L.h, n = w * h;
+    const size_t npix = (size_t)n;
+    dim3 b2(32, 8);
+    // ---- integer label ranges of both views and their hulls (one host round trip: the layout depends on them)
+    short *lo[2], *hi[2];
+    for (int vi = 0; vi < 2; vi++) { lo[vi] = arena_take<short>(s, npix); hi[vi] = arena_take<short>(s, npix); }
+    uint64_t *cen_half[2] = {nullptr, nullptr};
+    float *shifted = nullptr;
+    if (zoom == 2) { cen_half[0] = arena_take<uint64_t>(s, npix); cen_half[1] = arena_take<uint64_t>(s, npix); shifted = arena_take<float>(s, npix); }
+    float *tl = arena_take<float>(s, npix), *tr = arena_take<float>(s, npix);
+    int *lab = arena_take<int>(s, npix), *area = arena_take<int>(s, npix);
+    if (!area) return fail(S2PB_ERR_NOMEM, "pyramid arena exhausted");
+    // hull accumulators live in device memory (atomics on mapped host memory need PCIe atomics); copied back once
+    int *d_hull = ctx->d_scratch;
+    const int hull_init[4] = {0x7fffffff, (int)0x80000000, 0x7fffffff, (int)0x80000000};
+    CK(cudaMemcpyAsync(d_hull, hull_init, sizeof hull_init, cudaMemcpyHostToDevice, st));
+    label_ranges_kernel<<<(n + 255) / 256, 256, 0, st>>>(L.dminL, L.dmaxL, n, (float)zoom, lo[0], hi[0], d_hull);
+    label_ranges_kernel<<<(n + 255) / 256, 256, 0, st>>>(L.dminR, L.dmaxR, n, (float)zoom, lo[1], hi[1], d_hull + 2);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    int hull[4];
+    CK(cudaMemcpyAsync(hull, d_hull, sizeof hull, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int gminv[2] = {hull[0], hull[2]}, gmaxv[2] = {hull[1], hull[3]};
+    int D = 0;
+    for (int vi = 0; vi < 2; vi++) {
+        if (gminv[vi] < -16000 || gmaxv[vi] > 16000) return fail(S2PB_ERR_ARG, "label range out of the int16 domain");
+        int d = gmaxv[vi] - gminv[vi] + 1; if (d > D) D = d;
+    }
+    int LPL = lpl_for(D);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "a %dx%d level needs %d labels in its dense volume; 512 are supported", w, h, D);
+    int rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir);
+    if (rc != S2PB_OK) return rc;
+    TRACE(st, "level %dx%d zoom %d: hull L [%d,%d] R [%d,%d] -> LPL %d", w, h, zoom, gminv[0], gmaxv[0], gminv[1], gmaxv[1], LPL);
+    float lut_h[64];
+    const float *lut = nullptr;
+    if (cost_lut(p->census_win, lut_h)) { CK(cudaMemcpyAsync(s.lut, lut_h, sizeof lut_h, cudaMemcpyHostToDevice, st)); lut = s.lut; }
+    // ---- census (and, for ZOOMFACTOR 2, of the half-pixel shifted matched images)
+    const float *img[2] = {L.u, L.v};
+    for (int vi = 0; vi < 2; vi++) {
+        census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(img[vi], w, h, p->census_win / 2, s.v[vi].census);
+        ctx->launches++;
+    }
+    if (zoom == 2) {
+        for (int vi = 0; vi < 2; vi++) {      // cen_half[vi] = census(shift(img[vi], 1/2))
+            dct_shift_kernel<<<h, 256, (size_t)7 * w * sizeof(double), st>>>(img[vi], shifted, w, 0.5f);
+            census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(shifted, w, h, p->census_win / 2, cen_half[vi]);
+            ctx->launches += 2;
+        }
+    }
+    CK(cudaGetLastError());
+    for (int vi = 0; vi < 2; vi++) {
+        s.v[vi].lo = lo[vi]; s.v[vi].hi = hi[vi];
+        rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census, w, h, lo[vi], hi[vi], gminv[vi], s.v[vi].C, st,
+                         zoom == 2 ? cen_half[1 - vi] : nullptr, zoom);
+        if (rc != S2PB_OK) return rc;
+    }
+    TRACE(st, "  census + cost");
+    rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1 / (float)zoom, p->P2, p->ndir, p->tsgm, lut, st);   // mgm_multiscale.cc:194-202
+    if (rc != S2PB_OK) return rc;
+    TRACE(st, "  aggregate");
+    for (int vi = 0; vi < 2; vi++) {
+        WtaParams W;
+        fill_wta(W, s.v[vi], p->ndir, gminv[vi], p, lut, npix);
+        W.inv_zoom_div = (float)zoom;
+        rc = launch_wta(ctx, LPL, W, st);
+        if (rc != S2PB_OK) return rc;
+    }
+    TRACE(st, "  wta");
+    // ---- post filters of mgm_call (mgm_multiscale.cc:310-334)
+    float *dl = s.v[0].disp, *dr = s.v[1].disp, *xl = s.v[0].tmp, *xr = s.v[1].tmp;
+    if (p->median > 0) {
+        median_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dl, xl, w, h, p->median);
+        median_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dr, xr, w, h, p->median);
+        ctx->launches += 2;
+        float *t = dl; dl = xl; xl = t; t = dr; dr = xr; xr = t;
+    }
+    const bool cc = p->remove_small_cc > 0;
+    float *lrL = cc ? tl : L.dl, *lrR = cc ? tr : L.dr;
+    if (p->lr_mode == 1) {
+        lrcheck_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dr, dl, lrR, w, h, p->lr_tau);
+        lrcheck_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dl, dr, lrL, w, h, p->lr_tau);
+        ctx->launches += 2;
+    } else {
+        CK(cudaMemcpyAsync(lrL, dl, npix * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(lrR, dr, npix * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    TRACE(st, "  median / lr");
+    if (cc) {
+        rc = launch_remove_small_cc(ctx, lrL, L.dl, w, h, p->remove_small_cc, lab, area, st);
+        if (rc != S2PB_OK) return rc;
+        rc = launch_remove_small_cc(ctx, lrR, L.dr, w, h, p->remove_small_cc, lab, area, st);
+        if (rc != S2PB_OK) return rc;
+    }
+    TRACE(st, "  remove_small_cc");
+    CK(cudaMemcpyAsync(L.conf, s.v[0].conf, npix * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaGetLastError());
+    return S2PB_OK;
+}
+
+// main() of mgm_multi (main_mgm_multi.cc:88-256) + recursive_multiscale (mgm_multiscale.cc:339-410)
+static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *d_im2, int w, int h, int dmin, int dmax,
+                             const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_dispR, cudaStream_t st)
+{
+    const int n = w * h;
+    dim3 b2(32, 8);
+    // pyramid shape: downsample while max > 100, min > 50 and scale < -S (mgm_multiscale.cc:362)
+    std::vector<Level> lv(1);
+    lv[0].w = w; lv[0].h = h;
+    while ((int)lv.size() - 1 < p->scales) {
+        const Level &c = lv.back();
+        if (!((c.w > c.h ? c.w : c.h) > 100 && (c.w < c.h ? c.w : c.h) > 50)) break;
+        Level nx; nx.w = (c.w + 1) / 2; nx.h = (c.h + 1) / 2;
+        lv.push_back(nx);
+    }
+    size_t need = 0;
+    for (auto &L : lv) need += (size_t)L.w * L.h * 4 * 9 + 9 * 256;
+    need += (size_t)n * (4 * 12 + 2 * 4 + 8 * 2 + 4 * 2) * 2 + (1 << 20);     // scratch of the mgm_calls (two at full size)
+    int rc = arena_reset(s, need);
+    if (rc != S2PB_OK) return rc;
+    for (auto &L : lv) {
+        size_t m = (size_t)L.w * L.h;
+        L.u = arena_take<float>(s, m); L.v = arena_take<float>(s, m);
+        L.dminL = arena_take<float>(s, m); L.dmaxL = arena_take<float>(s, m);
+        L.dminR = arena_take<float>(s, m); L.dmaxR = arena_take<float>(s, m);
+        L.dl = arena_take<float>(s, m); L.dr = arena_take<float>(s, m); L.conf = arena_take<float>(s, m);
+        if (!L.conf) return fail(S2PB_ERR_NOMEM, "pyramid arena exhausted");
+    }
+    s.timed = false;
+    // level 0: NaN -> 0, initial bounds (main_mgm_multi.cc:160-196; the sentinel for no-data is dmin in both views)
+    init_ranges_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_im1, n, (float)dmin, (float)dmax, (float)dmin, lv[0].u, lv[0].dminL, lv[0].dmaxL);
+    init_ranges_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_im2, n, (float)-dmax, (float)-dmin, (float)dmin, lv[0].v, lv[0].dminR, lv[0].dmaxR);
+    ctx->launches += 2;
+    const GaussTaps T = gauss_taps(0.8f);
+    for (size_t l = 0; l + 1 < lv.size(); l++) {
+        Level &a = lv[l], &b = lv[l + 1];
+        dim3 g = grid2d(b.w, b.h, b2);
+        downsample2x_kernel<<<g, b2, 0, st>>>(a.u, a.w, a.h, T, b.u, b.w, b.h);
+        downsample2x_kernel<<<g, b2, 0, st>>>(a.v, a.w, a.h, T, b.v, b.w, b.h);
+        downsample2x_disp_kernel<<<g, b2, 0, st>>>(a.dminL, a.w, a.h, 0, b.dminL, b.w, b.h);
+        downsample2x_disp_kernel<<<g, b2, 0, st>>>(a.dmaxL, a.w, a.h, 1, b.dmaxL, b.w, b.h);
+        downsample2x_disp_kernel<<<g, b2, 0, st>>>(a.dminR, a.w, a.h, 0, b.dminR, b.w, b.h);
+        downsample2x_disp_kernel<<<g, b2, 0, st>>>(a.dmaxR, a.w, a.h, 1, b.dmaxR, b.w, b.h);
+        ctx->launches += 6;
+    }
+    CK(cudaGetLastError());
+    const size_t arena_mark = s.arena_off;
+    for (int l = (int)lv.size() - 1; l >= 0; l--) {
+        Level &L = lv[l];
+        if (l + 1 < (int)lv.size()) {          // upsample2x_disp (mgm_multiscale.cc:36-48): slack 8, radius 4, then zoom_nn x2
+            Level &c = lv[l + 1];
+            s.arena_off = arena_mark;
+            size_t m = (size_t)c.w * c.h;
+            float *omin = arena_take<float>(s, m), *omax = arena_take<float>(s, m);
+            const float *disp2[2] = {c.dl, c.dr};
+            float *fmin[2] = {L.dminL, L.dminR}, *fmax[2] = {L.dmaxL, L.dmaxR};
+            for (int vi = 0; vi < 2; vi++) {
+                update_ranges_kernel<<<grid2d(c.w, c.h, b2), b2, 0, st>>>(disp2[vi], 2.f, c.w, c.h, nullptr, nullptr, fmin[vi], fmax[vi],
+                                                                       L.w, L.h, 8.f, 4, omin, omax);
+                zoom2_kernel<<<grid2d(L.w, L.h, b2), b2, 0, st>>>(omin, c.w, fmin[vi], L.w, L.h);
+                zoom2_kernel<<<grid2d(L.w, L.h, b2), b2, 0, st>>>(omax, c.w, fmax[vi], L.w, L.h);
+                ctx->launches += 3;
+            }
+            CK(cudaGetLastError());
+        }
+        s.arena_off = arena_mark;
+        rc = mgm_call_level(ctx, s, L, 1, p, st);
+        if (rc != S2PB_OK) return rc;
+    }
+    Level &L0 = lv[0];
+    if (d_conf) CK(cudaMemcpyAsync(d_conf, L0.conf, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));   // the ZOOM=1 call's consensus
+    if (p->subpix > 1) {                       // main_mgm_multi.cc:203-209: bounds = result +-2 over 9x9, labels = half pixels
+        s.arena_off = arena_mark;
+        float *a = arena_take<float>(s, n), *b = arena_take<float>(s, n), *c = arena_take<float>(s, n), *d = arena_take<float>(s, n);
+        const size_t mark2 = s.arena_off;
+        update_ranges_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(L0.dl, 1.f, w, h, L0.dminL, L0.dmaxL, L0.dminL, L0.dmaxL, w, h, 2.f, 4, a, b);
+        update_ranges_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(L0.dr, 1.f, w, h, L0.dminR, L0.dmaxR, L0.dminR, L0.dmaxR, w, h, 2.f, 4, c, d);
+        ctx->launches += 2;
+        L0.dminL = a; L0.dmaxL = b; L0.dminR = c; L0.dmaxR = d;
+        s.arena_off = mark2;
+        rc = mgm_call_level(ctx, s, L0, p->subpix, p, st);
+        if (rc != S2PB_OK) return rc;
+    }
+    float *outL = d_disp;
+    if (p->lr_mode == 2) {                     // main_mgm_multi.cc:212-217
+        s.arena_off = arena_mark;
+        float *tr = arena_take<float>(s, n);
+        lrcheck_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(L0.dr, L0.dl, tr, w, h, p->lr_tau);
+        lrcheck_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(L0.dl, L0.dr, outL, w, h, p->lr_tau);
+        ctx->launches += 2;
+        if (d_dispR) CK(cudaMemcpyAsync(d_dispR, tr, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+        CK(cudaMemcpyAsync(outL, L0.dl, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        if (d_dispR) CK(cudaMemcpyAsync(d_dispR, L0.dr, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    nan_restore_kernel<<<(n + 255) / 256, 256, 0, st>>>(outL, d_im1, n);
+    ctx->launches++;
+    if (d_dispR) { nan_restore_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_dispR, d_im2, n); ctx->launches++; }
+    if (d_mask) { rejection_mask_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(outL, d_im1, d_im2, w, h, d_mask); ctx->launches++; }
+    CK(cudaGetLastError());
+    return S2PB_OK;
+}
+
 // ------------------------------------------------------------------ the matcher (device level)
 
 static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *d_im2, int w, int h, int dmin, int dmax,
                        const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_dispR, cudaStream_t st,
                        int nodata_hint)
 {
+    if (p->scales >= 0) return mgm_multi_enqueue(ctx, s, d_im1, d_im2, w, h, dmin, dmax, p, d_disp, d_conf, d_mask, d_dispR, st);
     const size_t npix = (size_t)w * h;
     const int n = (int)npix;
     if (nodata_hint < 0) {     // unknown: look (costs one stream synchronisation)
@@ -551,11 +839,7 @@ static int mgm_host_enqueue(s2pb_ctx *ctx, Slot &s, const float *im1, const floa
         for (size_t i = 0; i < npix; i++) { float v = im2[i]; dst[i] = v; acc |= (unsigned)(v != v); }
         sec_nodata = acc != 0;
     }
-    // size the workspace before touching d_in
-    int gminv[2], gmaxv[2];
-    int LPL = plan_labels(dmin, dmax, sec_nodata, gminv, gmaxv);
-    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "disparity range [%d,%d] needs more than the 512 labels supported", dmin, dmax);
-    rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir);
+    rc = slot_io_ensure(s, npix);
     if (rc != S2PB_OK) return rc;
     CK(cudaMemcpyAsync(s.d_in[0], s.h_in[0], npix * 4, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.d_in[1], s.h_in[1], npix * 4, cudaMemcpyHostToDevice, s.stream));
@@ -602,6 +886,8 @@ extern "C" int s2pb_reserve(s2pb_ctx *ctx, int nslots, int w, int h, int nlabels
         rc = slot_ensure(ctx, ctx->slots[i], w, h, 32 * LPL, 8);
         if (rc != S2PB_OK) return rc;
         rc = slot_host_ensure(ctx->slots[i], (size_t)w * h);
+        if (rc != S2PB_OK) return rc;
+        rc = slot_io_ensure(ctx->slots[i], (size_t)w * h);
         if (rc != S2PB_OK) return rc;
     }
     return S2PB_OK;
@@ -804,6 +1090,22 @@ extern "C" int s2pb_median(s2pb_ctx *ctx, const float *in, float *out, int w, in
     median_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(a.as<float>(), b.as<float>(), w, h, radius);
     ctx->launches++;
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, b.p, npix * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_remove_small_cc(s2pb_ctx *ctx, const float *in, float *out, int w, int h, int minarea)
+{
+    if (!ctx || !in || !out || w < 2 || h < 2) return fail(S2PB_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)w * h;
+    DevBuf a, b, l, r;
+    ALLOC(a, npix * 4); ALLOC(b, npix * 4); ALLOC(l, npix * 4); ALLOC(r, npix * 4);
+    cudaStream_t st = ctx->slots[0].stream;
+    CK(cudaMemcpyAsync(a.p, in, npix * 4, cudaMemcpyHostToDevice, st));
+    int rc = launch_remove_small_cc(ctx, a.as<float>(), b.as<float>(), w, h, minarea, l.as<int>(), r.as<int>(), st);
+    if (rc != S2PB_OK) return rc;
     CK(cudaMemcpyAsync(out, b.p, npix * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return S2PB_OK;

@@ -161,6 +161,13 @@ class Engine:
         _lib.check(self._L.s2pb_median(self._ctx, _fp(img), _fp(out), w, h, radius))
         return out
 
+    def remove_small_cc(self, img, minarea=25):
+        img = _f32(img)
+        h, w = img.shape
+        out = np.empty_like(img)
+        _lib.check(self._L.s2pb_remove_small_cc(self._ctx, _fp(img), _fp(out), w, h, int(minarea)))
+        return out
+
     def rejection_mask(self, disp, im1, im2):
         disp, im1, im2 = _f32(disp), _f32(im1), _f32(im2)
         h, w = disp.shape
