@@ -21,6 +21,9 @@ CASES = {
     "tsgm4_o4":   (48, 80, -8, 12, 104, 0.0, "", {"tsgm": 4, "ndir": 4}),
     "census3":    (48, 80, -8, 12, 105, 0.0, "", {"census_win": 3}),
     "nan_both":   (56, 88, -10, 9, 106, 0.07, "both", {}),   # depends on the DCT round trip of shift(): oracle-only
+    # `mgm_multi` with the flags of s2p/block_matching.py:269-308 (-S 6, SUBPIX=2, REMOVESMALLCC=25, TSGM=4)
+    "multi":      (120, 168, -18, 21, 107, 0.0, "", {"_algo": "mgm_multi"}),
+    "multi_s1":   (110, 150, -16, 12, 108, 0.0, "", {"_algo": "mgm_multi", "subpix": 1}),
 }
 
 
@@ -37,7 +40,9 @@ def main():
     out = os.path.dirname(os.path.abspath(__file__))
     for name in CASES:
         ref, sec, dmin, dmax, kw = inputs(name)
-        r = O.run_ref(ref, sec, dmin, dmax, O.mgm_params(dct_shift=1, **kw), threads=1)
+        kw = dict(kw)
+        mk = O.mgm_multi_params if kw.pop("_algo", "mgm") == "mgm_multi" else O.mgm_params
+        r = O.run_ref(ref, sec, dmin, dmax, mk(dct_shift=1, **kw), threads=1)
         np.savez_compressed(os.path.join(out, name + ".npz"), disp=r["disp"], conf=r["conf"].astype(np.uint8),
                             dispR=r["dispR"])
         print(name, ref.shape, "valid %.3f" % np.isfinite(r["disp"]).mean())

@@ -130,7 +130,7 @@ def test_timeout_and_errors(engine):
     assert e.value.code == _lib.ERR_ARG
 
 
-@pytest.mark.parametrize("name", ["plain", "wide", "nan_ref", "tsgm4_o4", "census3"])
+@pytest.mark.parametrize("name", ["plain", "wide", "nan_ref", "tsgm4_o4", "census3", "multi", "multi_s1"])
 def test_against_reference_golden_vectors(engine, name):
     """tests/golden/*.npz are outputs of the unmodified reference binary (tests/golden/make_golden.py)."""
     import os
@@ -140,7 +140,15 @@ def test_against_reference_golden_vectors(engine, name):
     from s2p_b200.engine import default_params
     ref, sec, dmin, dmax, kw = G.inputs(name)
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
-    out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm", **kw), want_right=True)
+    kw = dict(kw)
+    algo = kw.pop("_algo", "mgm")
+    out = engine.mgm(ref, sec, dmin, dmax, default_params(algo, **kw), want_right=True)
+    if name == "multi":      # half-pixel pass: see test_mgm_multi for why this one is held to the tolerance
+        both = np.isfinite(g["disp"]) & np.isfinite(out["disp"])
+        assert (np.isnan(g["disp"]) != np.isnan(out["disp"])).mean() < 2e-3
+        assert (np.abs(g["disp"][both] - out["disp"][both]) > SUBPIX_TOL).mean() < 2e-3
+        assert np.array_equal(out["conf"].astype(np.uint8), g["conf"])
+        return
     assert same(out["disp"], g["disp"]), "%d px differ from the reference" % nmismatch(out["disp"], g["disp"])
     assert np.array_equal(out["conf"].astype(np.uint8), g["conf"])
     if name != "nan_ref":      # see tests/test_oracle.py::test_identity_shift_equals_dct_shift_without_nodata

@@ -18,7 +18,11 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 def test_port_matches_golden(oracle, name):
     ref, sec, dmin, dmax, kw = G.inputs(name)
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(dct_shift=1, **kw))
+    kw = dict(kw)
+    if kw.pop("_algo", "mgm") == "mgm_multi":
+        d, c, dr = oracle.port.mgm_multi(ref, sec, dmin, dmax, oracle.mgm_multi_params(dct_shift=1, **kw))
+    else:
+        d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(dct_shift=1, **kw))
     assert same(d, g["disp"]), "%d px differ" % nmismatch(d, g["disp"])
     assert np.array_equal(c.astype(np.uint8), g["conf"])
     assert same(dr, g["dispR"])
@@ -72,6 +76,20 @@ def test_port_cost_volume_matches_reference_dump(oracle):
     hi = np.full((h, w), dmax, np.int32)
     C = oracle.port.costvolume(ref, sec, lo, hi, dmin, dmax - dmin + 1, dct_shift=1)
     assert dm == dmin and same(vol, C)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(subpix=1), dict(scales=1), dict(lr_mode=2), dict(remove_small_cc=0, tsgm=3)])
+def test_port_mgm_multi_matches_reference_binary(oracle, kw):
+    if not _have_ref(oracle):
+        pytest.skip("oracle/_ref/mgm_multi not built (needs /root/reference)")
+    from s2p_b200.synth import make_pair
+    h, w, dmin, dmax = 112, 140, -14, 17
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=55, nan_border=0.04)
+    P = oracle.mgm_multi_params(dct_shift=1, **kw)
+    r = oracle.run_ref(ref, sec, dmin, dmax, P, threads=1)
+    d, c, dr = oracle.port.mgm_multi(ref, sec, dmin, dmax, P)
+    assert same(d, r["disp"]), "%d px differ" % nmismatch(d, r["disp"])
+    assert same(c, r["conf"]) and same(dr, r["dispR"])
 
 
 def test_reference_sample_pair(oracle):
