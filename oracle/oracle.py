@@ -242,3 +242,19 @@ def read_costvolume_dump(path):
         nx, ny, nd, dmin = np.frombuffer(f.read(16), np.int32)
         vol = np.frombuffer(f.read(), np.float32).reshape(ny, nx, nd)
     return vol, int(dmin)
+
+
+def run_ref_homography(src, H, w, h, binary="homography_ref", workdir=None):
+    """Run the reference resampler (oracle/_ref/homography_ref: the unmodified LibHomography sources behind
+    oracle/homography_harness.cpp) on an in-memory image.  -> float32 (h, w) array."""
+    exe = os.path.join(REF_DIR, binary)
+    tmp = workdir or tempfile.mkdtemp(prefix="s2pb_hom_")
+    a, b = os.path.join(tmp, "src.pfm"), os.path.join(tmp, "out.pfm")
+    write_pfm(a, src)
+    hs = " ".join(repr(float(x)) for x in np.asarray(H, dtype=np.float64).ravel())
+    subprocess.run([exe, a, hs, b, str(int(w)), str(int(h))], check=True, stdout=subprocess.DEVNULL)
+    return read_pfm(b)
+
+
+def have_ref_homography():
+    return os.access(os.path.join(REF_DIR, "homography_ref"), os.X_OK)

@@ -34,6 +34,15 @@ def read_band(path):
     return np.ascontiguousarray(a.astype(np.float32))
 
 
+def read_window(path, x, y, w, h):
+    """-> float32 array of the w x h window at (x, y) of the first band."""
+    if _HAVE_RASTERIO:
+        from rasterio.windows import Window
+        with rasterio.open(path, "r") as f:
+            return np.ascontiguousarray(f.read(1, window=Window(x, y, w, h)).astype(np.float32))
+    return np.ascontiguousarray(read_band(path)[y:y + h, x:x + w])
+
+
 def image_size(path):
     """-> (width, height)"""
     if _HAVE_RASTERIO:

@@ -1,0 +1,76 @@
+"""Rectification warp against the reference's own resampler.
+
+The checker is oracle/_ref/homography_ref: the UNMODIFIED LibHomography / LibImages sources of the reference
+compiled in place behind oracle/homography_harness.cpp.  The reference is float32 + SSE and is built with
+-O3 -march=native, so its own output depends on FMA contraction: two builds of the same sources
+(oracle/_ref/homography_ref vs homography_ref_nofma) differ by up to 6e-5 of the dynamic range on these inputs.
+The tolerance below is set from that spread: |ours - reference| <= 1e-4 * max|src| on every pixel, and the
+NaN (outside-the-source) masks are identical except for pixels lying exactly on the source boundary."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+
+def _src(h=300, w=400, seed=0, nan=True):
+    from s2p_b200.synth import _blur
+    rng = np.random.default_rng(seed)
+    a = _blur(rng.integers(0, 4096, size=(h, w)).astype(np.float64)).astype(np.float32)
+    if nan:
+        a[:20, :30] = np.nan
+    return a
+
+
+def _rot(th, s, tx, ty):
+    c, si = np.cos(th) * s, np.sin(th) * s
+    return np.array([[c, -si, tx], [si, c, ty], [0, 0, 1.0]])
+
+
+CASES = {
+    "identity": np.eye(3),
+    "rot10": _rot(0.17, 1.0, 30, -40),
+    "rot78_shrink": _rot(1.36, 0.9885, 250, -60),          # the fixtures' H_sec: min singular value 0.9885 -> AA branch
+    "zoom_out": _rot(0.05, 0.6, 5, 5),
+    "zoom_in": _rot(-0.1, 1.7, -60, 20),
+    "perspective": np.array([[1.02, 0.03, -10], [0.01, 0.97, 5], [1e-5, -2e-5, 1]]),
+    "shifted_crop": _rot(0.02, 1.0, -150, -100),           # needed ROI is a strict sub-window of the source
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_warp_matches_reference(engine, oracle, name):
+    if not oracle.have_ref_homography():
+        pytest.skip("oracle/_ref/homography_ref not built")
+    src = _src()
+    H = CASES[name]
+    ow, oh = 256, 200
+    ref = oracle.run_ref_homography(src, H, ow, oh)
+    got = engine.homography(src, H, ow, oh)
+    assert got.shape == ref.shape == (oh, ow)
+    nan_diff = int((np.isnan(ref) != np.isnan(got)).sum())
+    assert nan_diff <= max(2, ref.size // 5000), "%d NaN-mask mismatches" % nan_diff
+    both = np.isfinite(ref) & np.isfinite(got)
+    assert both.any()
+    err = np.abs(ref[both] - got[both]).max()
+    assert err <= REL_TOL * np.nanmax(np.abs(src)), "max abs error %g" % err
+
+
+def test_dropin_file_contract(engine, oracle, tmp_path):
+    if not oracle.have_ref_homography():
+        pytest.skip("oracle/_ref/homography_ref not built")
+    import subprocess
+    from s2p_b200 import common, rasterio_compat as rio
+    src = _src(260, 340, seed=3, nan=False)
+    im, out = str(tmp_path / "im.tif"), str(tmp_path / "rect.tif")
+    rio.write_float_tiff(im, src)
+    H = _rot(0.12, 1.0, 20, -15)
+    assert common.image_apply_homography(out, im, H, 200, 150) is None
+    got = rio.read_band(out)
+    ref = oracle.run_ref_homography(src, H, 200, 150)
+    assert got.shape == (150, 200)
+    assert int((np.isnan(ref) != np.isnan(got)).sum()) <= 2
+    both = np.isfinite(ref) & np.isfinite(got)
+    assert np.abs(ref[both] - got[both]).max() <= REL_TOL * np.abs(src).max()
+    with pytest.raises(subprocess.CalledProcessError):      # the binary exits with "empty roi"
+        common.image_apply_homography(out, im, _rot(0, 1.0, 5000, 5000), 50, 50)
