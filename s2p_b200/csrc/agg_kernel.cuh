@@ -151,7 +151,7 @@ template <int LPL> __device__ __forceinline__ HalfPack<LPL> ld_cost(const __half
 __device__ __forceinline__ float cost_value(unsigned short hbits, const float *__restrict__ lut)
 {
     float c = __half2float(__ushort_as_half(hbits));
-    if (lut != nullptr && c < 64.f) c = lut[(int)c];
+    if (lut != nullptr && c >= 0.f && c < 64.f) c = lut[(int)c];
     return c;
 }
 
@@ -419,7 +419,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
 #pragma unroll
         for (int e = 0; e < LPL; e++) {
             float cc = __half2float(__ushort_as_half(cp.h[e]));
-            if (SCALED) { if (cc < 64.f) cc = lut[(int)cc]; }
+            if (SCALED) { if (cc >= 0.f && cc < 64.f) cc = lut[(int)cc]; }   // an idle scanline reads unstaged shared memory: never index with it
             c[e] = cc;
         }
     };

@@ -169,11 +169,14 @@ __device__ __forceinline__ void parabola3(float v0, float v1, float v2, float &v
 // One warp per pixel: S = (L0+L1+...+L_{ndir-1}) - (ndir-1) C in pass order (dvec.cc:110-118,
 // mgm_core.cc:1041-1042), first strict minimum over finite S (:1044-1048), consensus (:1054-1057),
 // V-fit / parabola on S[o-1..o+1] when o-1 >= lo and o+2 <= hi (mgm_refine.h:67-84).
+// 128-thread CTAs capped at 56 registers for LPL <= 4: one of them still fits on an SM next to the two resident
+// CTAs of the (issue-bound) aggregation kernel of the NEXT tile, so this memory-bound kernel overlaps it.
+constexpr int kWtaThreads = 128;
 template <int LPL>
-__global__ void wta_kernel(const WtaParams P)
+__global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 128) wta_kernel(const WtaParams P)
 {
     constexpr int DP = 32 * LPL;
-    __shared__ float sS[8][DP];
+    __shared__ float sS[kWtaThreads / 32][DP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t p = warp; p < P.npix; p += nwarps) {
@@ -181,23 +184,27 @@ __global__ void wta_kernel(const WtaParams P)
         int am[kMaxPasses];       // per pass: LAST slot attaining the pass minimum (mgm_core.cc:1015-1019)
 #pragma unroll
         for (int e = 0; e < LPL; e++) s[e] = 0.f;
-        // all passes' vectors are requested before any is consumed (memory-level parallelism)
-        float v[kMaxPasses][LPL];
+        // the passes' vectors are requested four at a time before any is consumed (memory-level parallelism
+        // within the register budget that lets this kernel share an SM with the aggregation kernel)
 #pragma unroll
-        for (int d = 0; d < kMaxPasses; d++)
-            if (d < P.ndir) ld_vec_cg<LPL>(P.L[d] + p * DP + lane * LPL, v[d]);
+        for (int g = 0; g < kMaxPasses; g += 4) {
+            float v[4][LPL];
 #pragma unroll
-        for (int d = 0; d < kMaxPasses; d++) {
-            am[d] = -1;
-            if (d < P.ndir) {
-                float lm = v[d][0];
+            for (int q = 0; q < 4; q++)
+                if (g + q < P.ndir) ld_vec_cg<LPL>(P.L[g + q] + p * DP + lane * LPL, v[q]);
 #pragma unroll
-                for (int e = 1; e < LPL; e++) lm = fminf(lm, v[d][e]);
-                const float md = warp_min_f32(lm);
-                int a = -1;
+            for (int q = 0; q < 4; q++) {
+                am[g + q] = -1;
+                if (g + q < P.ndir) {
+                    float lm = v[q][0];
 #pragma unroll
-                for (int e = 0; e < LPL; e++) { if (v[d][e] == md) a = lane * LPL + e; s[e] += v[d][e]; }
-                am[d] = __reduce_max_sync(0xffffffffu, a);
+                    for (int e = 1; e < LPL; e++) lm = fminf(lm, v[q][e]);
+                    const float md = warp_min_f32(lm);
+                    int a = -1;
+#pragma unroll
+                    for (int e = 0; e < LPL; e++) { if (v[q][e] == md) a = lane * LPL + e; s[e] += v[q][e]; }
+                    am[g + q] = __reduce_max_sync(0xffffffffu, a);
+                }
             }
         }
         HalfPack<LPL> cp = ld_cost<LPL>(P.C + p * DP + lane * LPL);
@@ -299,6 +306,31 @@ __global__ void lrcheck_kernel(const float *__restrict__ dx, const float *__rest
         } else r = __int_as_float(0x7fc00000);
     }
     out[i] = r;
+}
+
+// mindiff, stereo_utils.cc:93-124: inside the image minus a border of half a window, a pixel whose disparity
+// differs by more than tau from the disparity of the window's lowest-cost finite pixel becomes NaN.  `corr` is
+// the OTHER view's refined cost image, indexed with this view's coordinates, exactly as the reference does
+// (mgm_multiscale.cc:318-319).  Window scan: x offset outer, y offset inner, strict comparison.
+__global__ void mindiff_kernel(const float *__restrict__ disp, const float *__restrict__ corr, float *__restrict__ out,
+                               int w, int h, int win, float tau)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int wl = win / 2, wr = (win % 2 == 0) ? win / 2 - 1 : win / 2;
+    const size_t o = (size_t)y * w + x;
+    float d = disp[o];
+    if (y >= wl && y < h - wr && x >= wl && x < w - wr) {
+        float mincorr = S2PB_INF, mindisp = 0.f;
+        for (int i = -wl; i <= wr; i++)
+            for (int j = -wl; j <= wr; j++) {
+                const size_t q = (size_t)(y + j) * w + (x + i);
+                const float c = corr[q], dd = disp[q];
+                if (mincorr > c && isfinite(dd)) { mincorr = c; mindisp = dd; }
+            }
+        if (fabsf(d - mindisp) > tau) d = __int_as_float(0x7fc00000);
+    }
+    out[o] = d;
 }
 
 // main_mgm.cc:231-236 : no-data pixels of the view's own image get NaN

@@ -305,7 +305,6 @@ static int check_params(const s2pb_mgm_params *p, int w, int h, int dmin, int dm
     if (p->subpix != 1 && p->subpix != 2) return fail(S2PB_ERR_UNSUPPORTED, "SUBPIX must be 1 or 2");
     if (p->scales < 0 && p->subpix != 1) return fail(S2PB_ERR_ARG, "SUBPIX=2 only exists in mgm_multi (scales >= 0)");
     if (p->scales < 0 && p->remove_small_cc > 0) return fail(S2PB_ERR_UNSUPPORTED, "REMOVESMALLCC is only wired into the mgm_multi path");
-    if (p->mindiff >= 0) return fail(S2PB_ERR_UNSUPPORTED, "MINDIFF is not implemented in this build");
     if (p->lr_mode < 0 || p->lr_mode > 2) return fail(S2PB_ERR_ARG, "TESTLRRL must be 0, 1 or 2");
     if (p->scales < 0 && p->lr_mode == 2) return fail(S2PB_ERR_ARG, "TESTLRRL=2 only exists in mgm_multi");
     if (p->scales >= 0 && w > 4000) return fail(S2PB_ERR_UNSUPPORTED, "mgm_multi tiles wider than 4000 px are not supported");
@@ -393,7 +392,7 @@ template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t 
 }
 template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStream_t st)
 {
-    wta_kernel<LPL><<<sm * 8, 256, 0, st>>>(P);
+    wta_kernel<LPL><<<sm * 16, kWtaThreads, 0, st>>>(P);
 }
 #define LPL_SWITCH(LPL, CALL)                                                             \
     switch (LPL) {                                                                        \
@@ -568,6 +567,11 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
         median_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dr, xr, w, h, p->median);
         ctx->launches += 2;
         float *t = dl; dl = xl; xl = t; t = dr; dr = xr; xr = t;
+    }
+    if (p->mindiff >= 0) {
+        mindiff_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dl, s.v[1].cost, xl, w, h, p->census_win, p->mindiff);
+        ctx->launches++;
+        float *t = dl; dl = xl; xl = t;
     }
     const bool cc = p->remove_small_cc > 0;
     float *lrL = cc ? tl : L.dl, *lrR = cc ? tr : L.dr;
@@ -761,6 +765,11 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
         median_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dr, tr, w, h, p->median);
         ctx->launches += 2;
         float *x = dl; dl = tl; tl = x; x = dr; dr = tr; tr = x;
+    }
+    if (p->mindiff >= 0) {      // mgm_multiscale.cc:318-319: only the left map, against the right view's cost image
+        mindiff_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dl, s.v[1].cost, tl, w, h, p->census_win, p->mindiff);
+        ctx->launches++;
+        float *x = dl; dl = tl; tl = x;
     }
     float *outL = d_disp, *outR = d_dispR ? d_dispR : tr;
     if (p->lr_mode == 1) {

@@ -79,7 +79,8 @@ def test_mgm_end_to_end(engine, oracle, shape, dmin, dmax, nanb, seed):
 
 
 @pytest.mark.parametrize("kw", [dict(tsgm=4), dict(tsgm=2), dict(ndir=4), dict(census_win=3), dict(census_win=7),
-                                dict(median=0, lr_mode=0, refine=0), dict(median=2), dict(P1=4.0, P2=50.0)])
+                                dict(median=0, lr_mode=0, refine=0), dict(median=2), dict(P1=4.0, P2=50.0), dict(mindiff=1.0),
+                                dict(mindiff=0.5, median=0)])
 def test_mgm_options(engine, oracle, kw):
     h, w, dmin, dmax = 48, 90, -9, 14
     ref, sec, _ = make_pair(h, w, dmin, dmax, seed=21, nan_border=0.04)

@@ -49,7 +49,8 @@ def _have_ref(oracle):
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(tsgm=1), dict(tsgm=2), dict(tsgm=4), dict(ndir=4), dict(ndir=2),
-                                dict(census_win=3), dict(census_win=7), dict(median=0, lr_mode=0, refine=0), dict(median=2)])
+                                dict(census_win=3), dict(census_win=7), dict(median=0, lr_mode=0, refine=0), dict(median=2),
+                                dict(mindiff=1.0)])
 def test_port_matches_reference_binary(oracle, kw):
     if not _have_ref(oracle):
         pytest.skip("oracle/_ref/mgm not built (needs /root/reference)")
