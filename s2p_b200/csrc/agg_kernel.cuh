@@ -448,6 +448,54 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             L[e] = border ? c[e] : c[e] + acc;
         }
     };
+    // The same recursion for the warp's two scanlines at once: the float adds / multiplies / fmas of scanline A and
+    // scanline B are issued as packed f32x2 instructions (FADD2 / FMUL2 / FFMA2, sm_100), each lane of a pair
+    // rounding exactly like the scalar instruction; the min / min3 stay scalar.  (a*, b*) = neighbours of A, of B.
+    auto recurse2 = [&](const float (&cA)[LPL], const float (&cB)[LPL],
+                        const NbVec<LPL> &aA, const NbVec<LPL> &aB, const NbVec<LPL> &aC, const NbVec<LPL> &aE,
+                        const NbVec<LPL> &bA, const NbVec<LPL> &bB, const NbVec<LPL> &bC, const NbVec<LPL> &bE,
+                        bool borderA, bool borderB, float (&LA)[LPL], float (&LB)[LPL]) {
+        const float2 P1v = make_float2(P1, P1), P2v = make_float2(P2, P2);
+        const float2 mA = make_float2(aA.m, bA.m), mB = make_float2(aB.m, bB.m), mC = make_float2(aC.m, bC.m), mE = make_float2(aE.m, bE.m);
+        const float2 qA = __fadd2_rn(mA, P2v), qB = __fadd2_rn(mB, P2v), qC = __fadd2_rn(mC, P2v), qE = __fadd2_rn(mE, P2v);
+        const float2 nA = make_float2(-mA.x, -mA.y), nB = make_float2(-mB.x, -mB.y), nC = make_float2(-mC.x, -mC.y), nE = make_float2(-mE.x, -mE.y);
+        auto term = [&](const NbVec<LPL> &na, const NbVec<LPL> &nb, int e, const float2 q, const float2 negm) {
+            const float la = (e == 0) ? na.l : na.v[e - 1], ra = (e == LPL - 1) ? na.r : na.v[e + 1];
+            const float lb = (e == 0) ? nb.l : nb.v[e - 1], rb = (e == LPL - 1) ? nb.r : nb.v[e + 1];
+            const float2 v1 = __fadd2_rn(make_float2(fminf(la, ra), fminf(lb, rb)), P1v);
+            const float2 t = make_float2(fmin3f(na.v[e], v1.x, q.x), fmin3f(nb.v[e], v1.y, q.y));
+            return __fadd2_rn(t, negm);
+        };
+        const float2 half2v = make_float2(0.5f, 0.5f), quart = make_float2(0.25f, 0.25f);
+        const float r3 = 0.3333333432674407958984375f;
+        const float2 r3v = make_float2(r3, r3), m3v = make_float2(-3.0f, -3.0f);
+#pragma unroll
+        for (int e = 0; e < LPL; e++) {
+            float2 acc;
+            if constexpr (TYPE == 0) {
+                acc = term(aA, bA, e, qA, nA);
+                if (TSGM == 2) acc = __fmul2_rn(acc, half2v);
+                if (useCn) { float2 tt = term(aC, bC, e, qC, nC); if (TSGM == 2) tt = __fmul2_rn(tt, half2v); acc = __fadd2_rn(acc, tt); }
+                if (useB)  acc = __fadd2_rn(acc, term(aB, bB, e, qB, nB));
+                if (useE)  acc = __fadd2_rn(acc, term(aE, bE, e, qE, nE));
+            } else {
+                acc = term(aE, bE, e, qE, nE);
+                if (TSGM == 2) acc = __fmul2_rn(acc, half2v);
+                if (useB)  { float2 tt = term(aB, bB, e, qB, nB); if (TSGM == 2) tt = __fmul2_rn(tt, half2v); acc = __fadd2_rn(acc, tt); }
+                if (useCn) acc = __fadd2_rn(acc, term(aC, bC, e, qC, nC));
+                if (useA)  acc = __fadd2_rn(acc, term(aA, bA, e, qA, nA));
+            }
+            if constexpr (TSGM == 3) {            // exact x/3, see div3_exact
+                const float2 q0 = __fmul2_rn(acc, r3v);
+                const float2 rr = __ffma2_rn(m3v, q0, acc);
+                acc = __ffma2_rn(rr, r3v, q0);
+            }
+            if constexpr (TSGM == 4) acc = __fmul2_rn(acc, quart);
+            const float2 L2 = __fadd2_rn(make_float2(cA[e], cB[e]), acc);
+            LA[e] = borderA ? cA[e] : L2.x;
+            LB[e] = borderB ? cB[e] : L2.y;
+        }
+    };
     auto vec_min = [&](const float (&L)[LPL]) {
         float lm = L[0];
 #pragma unroll
@@ -480,16 +528,17 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             cp_async_wait<S>();                               // the groups of this step's pixels have landed
             __syncwarp();
             float cA[LPL], cB[LPL], LA[LPL], LB[LPL];
-            load_cost(cstA + (iA & (kStage - 1)) * DP, cA);
-            load_cost(cstB + (iB & (kStage - 1)) * DP, cB);
+#pragma unroll
+            for (int e = 0; e < LPL; e++) cA[e] = cB[e] = 0.f;
+            if (actA) load_cost(cstA + (iA & (kStage - 1)) * DP, cA);     // an idle scanline's slot is not staged yet
+            if (actB) load_cost(cstB + (iB & (kStage - 1)) * DP, cB);
             if (prevA && actA) {
                 if (useE) { if (iA == 0) fetch_prev(0, xC); if (iA + 1 < nI) fetch_prev(iA + 1, xE); }
                 else fetch_prev(iA, xC);
             }
             const bool borderA = (sA == 0) || (iA == 0) || (iA == nI - 1);
             const bool borderB = (iB == 0) || (iB == nI - 1);
-            recurse(cA, inlineA, xB, xC, xE, borderA, LA);
-            recurse(cB, wAB, hNew, hC, hE, borderB, LB);
+            recurse2(cA, cB, inlineA, xB, xC, xE, wAB, hNew, hC, hE, borderA, borderB, LA, LB);
             const float mAm = vec_min(LA), mBm = vec_min(LB);
             if (actA) {
 #pragma unroll
@@ -535,7 +584,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
 }
 
 template <int LPL, int TSGM, bool SCALED>
-__global__ void __launch_bounds__(kAggThreads) __maxnreg__((LPL <= 4) ? 128 : 255) aggregate_kernel(const __grid_constant__ AggParams P)
+__global__ void __launch_bounds__(kAggThreads) __maxnreg__((LPL <= 4) ? 112 : 255) aggregate_kernel(const __grid_constant__ AggParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_item;

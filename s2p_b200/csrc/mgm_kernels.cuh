@@ -55,9 +55,9 @@ __global__ void has_nan_kernel(const float *__restrict__ in, int n, int *flag)
 // finite, the whole range is set to 0.  Slots outside [lo,hi] stay +INF.
 // With ZOOMFACTOR = 2 (mgm_costvolume.cc:145-154) label o compares cu(x) with the census of the matched image
 // shifted by (o mod 2)/2 pixel, at column x + floor(o/2): cv = shift 0, cv1 = shift 1/2.
-template <int LPL>
+template <int LPL, bool ZOOM2>
 __global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__restrict__ cv, const uint64_t *__restrict__ cv1,
-                            int zoom, int w, int h,
+                            int w, int h,
                             const short *__restrict__ lo, const short *__restrict__ hi, int gmin, __half *__restrict__ C)
 {
     constexpr int DP = 32 * LPL;
@@ -78,7 +78,7 @@ __global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__r
             if (o >= l && o <= hgh) {
                 int q = x + o;
                 const uint64_t *codes = cv;
-                if (zoom == 2) { q = x + (o >> 1); if (o & 1) codes = cv1; }      // floor(o/2), goodmod(o,2)
+                if (ZOOM2) { q = x + (o >> 1); if (o & 1) codes = cv1; }          // floor(o/2), goodmod(o,2)
                 if (q >= 0 && q < w) { v = (float)__popcll(a ^ codes[row + q]); anyfinite = true; }
             }
             c[e] = v;

@@ -388,7 +388,8 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
 template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t *cv, const uint64_t *cv1, int zoom, int w, int h,
                                              const short *lo, const short *hi, int gmin, __half *C, int sm, cudaStream_t st)
 {
-    cost_kernel<LPL><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, zoom, w, h, lo, hi, gmin, C);
+    if (zoom == 2) cost_kernel<LPL, true><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
+    else cost_kernel<LPL, false><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
 }
 template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStream_t st)
 {
