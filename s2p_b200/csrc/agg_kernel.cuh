@@ -22,6 +22,7 @@
 // compiled with -fmad=false and every fused operation below is written explicitly.
 #pragma once
 #include <cuda_fp16.h>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -454,7 +455,8 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     auto recurse2 = [&](const float (&cA)[LPL], const float (&cB)[LPL],
                         const NbVec<LPL> &aA, const NbVec<LPL> &aB, const NbVec<LPL> &aC, const NbVec<LPL> &aE,
                         const NbVec<LPL> &bA, const NbVec<LPL> &bB, const NbVec<LPL> &bC, const NbVec<LPL> &bE,
-                        bool borderA, bool borderB, float (&LA)[LPL], float (&LB)[LPL]) {
+                        bool borderA, bool borderB, float (&LA)[LPL], float (&LB)[LPL], auto interior_c) {
+        constexpr bool INTERIOR = decltype(interior_c)::value;     // both pixels are interior: no border select
         const float2 P1v = make_float2(P1, P1), P2v = make_float2(P2, P2);
         const float2 mA = make_float2(aA.m, bA.m), mB = make_float2(aB.m, bB.m), mC = make_float2(aC.m, bC.m), mE = make_float2(aE.m, bE.m);
         const float2 qA = __fadd2_rn(mA, P2v), qB = __fadd2_rn(mB, P2v), qC = __fadd2_rn(mC, P2v), qE = __fadd2_rn(mE, P2v);
@@ -492,8 +494,8 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             }
             if constexpr (TSGM == 4) acc = __fmul2_rn(acc, quart);
             const float2 L2 = __fadd2_rn(make_float2(cA[e], cB[e]), acc);
-            LA[e] = borderA ? cA[e] : L2.x;
-            LB[e] = borderB ? cB[e] : L2.y;
+            LA[e] = (!INTERIOR && borderA) ? cA[e] : L2.x;
+            LB[e] = (!INTERIOR && borderB) ? cB[e] : L2.y;
         }
     };
     auto vec_min = [&](const float (&L)[LPL]) {
@@ -517,12 +519,15 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     // One lock-step pixel step.  Roles at step t: (xB, xC, xE) = window on A's previous scanline at A's
     // pixel-1, pixel, pixel+1; hNew = A's result of U steps ago (B's "B" neighbour; overwritten with A's new
     // result at the end of the step), hC / hE = A's results of U-1.. / 1 steps ago.
-    auto step = [&](const int t, NbVec<LPL> &xB, NbVec<LPL> &xC, NbVec<LPL> &xE, NbVec<LPL> &hNew, NbVec<LPL> &hC, NbVec<LPL> &hE) {
+    // FAST: both scanlines are live and at interior pixels (warp-uniform), which removes every activity / border /
+    // end-of-line predicate from the step; the slow variant handles ramp-up, ramp-down and the image border.
+    auto step = [&](auto fast_c, const int t, NbVec<LPL> &xB, NbVec<LPL> &xC, NbVec<LPL> &xE, NbVec<LPL> &hNew, NbVec<LPL> &hC, NbVec<LPL> &hE) {
+        constexpr bool FAST = decltype(fast_c)::value;
         const int iA = t - 2 * k * SKEW, iB = iA - SKEW;
-        const bool actA = liveA && iA >= 0 && iA < nI, actB = liveB && iB >= 0 && iB < nI;
+        const bool actA = FAST || (liveA && iA >= 0 && iA < nI), actB = FAST || (liveB && iB >= 0 && iB < nI);
         NbVec<LPL> &inlineA = useE ? hE : hC;                 // A's result of the previous step
-        if (iA - rsel * SKEW >= 0) stage_cost();              // my scanline is at pixel jc - S: stage pixel jc
-        if (iA >= 0) stage_prevband();
+        if (FAST || iA - rsel * SKEW >= 0) stage_cost();      // my scanline is at pixel jc - S: stage pixel jc
+        if (FAST || iA >= 0) stage_prevband();
         cp_async_commit();
         if (actA || actB) {
             cp_async_wait<S>();                               // the groups of this step's pixels have landed
@@ -532,13 +537,15 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             for (int e = 0; e < LPL; e++) cA[e] = cB[e] = 0.f;
             if (actA) load_cost(cstA + (iA & (kStage - 1)) * DP, cA);     // an idle scanline's slot is not staged yet
             if (actB) load_cost(cstB + (iB & (kStage - 1)) * DP, cB);
-            if (prevA && actA) {
+            if (FAST) {
+                if (useE) fetch_prev(iA + 1, xE); else fetch_prev(iA, xC);
+            } else if (prevA && actA) {
                 if (useE) { if (iA == 0) fetch_prev(0, xC); if (iA + 1 < nI) fetch_prev(iA + 1, xE); }
                 else fetch_prev(iA, xC);
             }
             const bool borderA = (sA == 0) || (iA == 0) || (iA == nI - 1);
             const bool borderB = (iB == 0) || (iB == nI - 1);
-            recurse2(cA, cB, inlineA, xB, xC, xE, wAB, hNew, hC, hE, borderA, borderB, LA, LB);
+            recurse2(cA, cB, inlineA, xB, xC, xE, wAB, hNew, hC, hE, borderA, borderB, LA, LB, fast_c);
             const float mAm = vec_min(LA), mBm = vec_min(LB);
             if (actA) {
 #pragma unroll
@@ -569,15 +576,22 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         }
         __syncthreads();
     };
+    // a step is FAST for this warp when A is at an interior pixel with B one SKEW behind, also interior
+    const bool can_fast = liveA && liveB && prevA;
+    const int fast_lo = 2 * k * SKEW + SKEW + 1, fast_hi = 2 * k * SKEW + nI - 2;     // t range: iB >= 1 and iA <= nI-2
+    auto do_step = [&](const int t, NbVec<LPL> &xB, NbVec<LPL> &xC, NbVec<LPL> &xE, NbVec<LPL> &hNew, NbVec<LPL> &hC, NbVec<LPL> &hE) {
+        if (can_fast && t >= fast_lo && t <= fast_hi) step(std::true_type{}, t, xB, xC, xE, hNew, hC, hE);
+        else step(std::false_type{}, t, xB, xC, xE, hNew, hC, hE);
+    };
 
     for (int t = 0; t < nsteps; t += U) {
         if constexpr (U == 2) {
-            step(t, x1, x0, x2, h0, h1, h2);
-            step(t + 1, x0, x1, x2, h1, h0, h2);
+            do_step(t, x1, x0, x2, h0, h1, h2);
+            do_step(t + 1, x0, x1, x2, h1, h0, h2);
         } else {
-            step(t, x1, x2, x0, h0, h1, h2);
-            step(t + 1, x2, x0, x1, h1, h2, h0);
-            step(t + 2, x0, x1, x2, h2, h0, h1);
+            do_step(t, x1, x2, x0, h0, h1, h2);
+            do_step(t + 1, x2, x0, x1, h1, h2, h0);
+            do_step(t + 2, x0, x1, x2, h2, h0, h1);
         }
     }
     cp_async_wait<0>();
