@@ -119,6 +119,13 @@ int s2pb_sync(s2pb_ctx *ctx);
 int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh,
                     const double H[9], float *dst, int dw, int dh);
 
+/* ---- n-view merge (a "next" row of SURVEY.md section 8f) ---------------------- */
+/* s2p.fusion.merge_n (s2p/fusion.py:25-68) from memory to memory: out = op_k(inputs[k] - offsets[k]) +
+ * mean(offsets), pixelwise in float64, stored as float32.  op: 0 average_if_close (NaN when
+ * nanmax - nanmin > threshold, else nanmedian; s2p/fusion.py:16-23), 1 nanmedian, 2 nanmean, 3 nanmin, 4 nanmax. */
+int s2pb_merge_n(s2pb_ctx *ctx, const float *const *inputs, const double *offsets, int n, int w, int h,
+                 int op, double threshold, float *out);
+
 /* ---- stage-level entry points (host buffers; used by the parity tests) ----- */
 /* census_tools.cc:127-153.  codes: w*h uint64, first neighbour in the top bit. */
 int s2pb_census(s2pb_ctx *ctx, const float *img, int w, int h, int win, uint64_t *codes);

@@ -8,6 +8,7 @@
 #include "mgm_kernels.cuh"
 #include "multiscale_kernels.cuh"
 #include "homography_kernels.cuh"
+#include "fusion_kernels.cuh"
 #include "agg_dispatch.h"
 
 #include <chrono>
@@ -1278,6 +1279,39 @@ extern "C" int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh, 
     int rc = map_image(ctx, st, roi.as<float>(), w, h, Hc, out.as<float>(), dw, dh, true, 0);
     if (rc != S2PB_OK) return rc;
     CK(cudaMemcpyAsync(dst, out.p, (size_t)dw * dh * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+// ------------------------------------------------------------------ n-view merge (section 8f)
+
+extern "C" int s2pb_merge_n(s2pb_ctx *ctx, const float *const *inputs, const double *offsets, int n, int w, int h, int op,
+                            double threshold, float *out)
+{
+    if (!ctx || !inputs || !offsets || !out || n < 1 || w < 1 || h < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    if (n > kMaxFusion) return fail(S2PB_ERR_UNSUPPORTED, "at most %d rasters can be merged", kMaxFusion);
+    if (op < FUSE_AVERAGE_IF_CLOSE || op > FUSE_NANMAX) return fail(S2PB_ERR_ARG, "unknown averaging operator %d", op);
+    CK(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)w * h;
+    cudaStream_t st = ctx->slots[0].stream;
+    DevBuf in, o;
+    ALLOC(in, npix * 4 * n);
+    ALLOC(o, npix * 4);
+    FusionParams P;
+    memset(&P, 0, sizeof P);
+    double s = 0;
+    for (int k = 0; k < n; k++) {
+        if (!inputs[k]) return fail(S2PB_ERR_ARG, "null raster %d", k);
+        P.in[k] = in.as<float>() + npix * k;
+        CK(cudaMemcpyAsync((void *)P.in[k], inputs[k], npix * 4, cudaMemcpyHostToDevice, st));
+        P.offset[k] = offsets[k];
+        s += offsets[k];                     // np.mean of a short list: plain left-to-right sum / n
+    }
+    P.n = n; P.op = op; P.threshold = threshold; P.mean_offset = s / n; P.npix = npix; P.out = o.as<float>();
+    fusion_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(P);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, o.p, npix * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return S2PB_OK;
 }

@@ -135,6 +135,24 @@ class Engine:
                                            Hm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _fp(out), int(w), int(h)))
         return out
 
+    # ------------------------------------------------------------------ n-view merge
+    FUSION_OPS = {"average_if_close": 0, "np.nanmedian": 1, "np.nanmean": 2, "np.nanmin": 3, "np.nanmax": 4}
+
+    def merge_n(self, rasters, offsets, averaging="average_if_close", threshold=1.0):
+        """Pixelwise merge of n equally sized rasters (s2p/fusion.py:25-68) -> float32 array."""
+        if averaging.startswith("numpy."):
+            averaging = "np." + averaging[6:]
+        if averaging not in self.FUSION_OPS:
+            raise NotImplementedError("averaging operator %r" % averaging)
+        rs = [_f32(r) for r in rasters]
+        n = len(rs)
+        h, w = rs[0].shape
+        ptrs = (ctypes.c_void_p * n)(*[r.ctypes.data for r in rs])
+        offs = (ctypes.c_double * n)(*[float(o) for o in offsets])
+        out = np.empty((h, w), np.float32)
+        _lib.check(self._L.s2pb_merge_n(self._ctx, ptrs, offs, n, w, h, self.FUSION_OPS[averaging], float(threshold), _fp(out)))
+        return out
+
     # ------------------------------------------------------------------ stages (parity tests)
     def census(self, img, win=5):
         img = _f32(img)

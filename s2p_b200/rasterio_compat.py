@@ -74,3 +74,14 @@ def write_mask_png(path, m):
         return
     from PIL import Image
     Image.fromarray(m, mode="L").save(path, format="PNG")
+
+
+def overwrite_band(path, a):
+    """Replace the content of the (single) band of an existing raster, keeping its metadata
+    (rasterio 'r+' as in s2p/fusion.py:65-66; without rasterio the file is rewritten as a plain TIFF)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if _HAVE_RASTERIO:
+        with rasterio.open(path, "r+") as f:
+            f.write(np.asarray([a]).astype("float32"))
+        return
+    write_float_tiff(path, a)

@@ -1,0 +1,55 @@
+"""n-view merge: the numpy restatement against the reference's own
+`average_if_close` (CPU), and the CUDA kernel against the restatement (GPU).  Bit-exact."""
+import numpy as np
+import pytest
+
+from util import same
+
+
+def _maps(n, h=37, w=53, seed=0):
+    rng = np.random.default_rng(seed)
+    base = rng.normal(100, 5, (h, w))
+    maps = [(base + rng.normal(0, 0.7, (h, w)) + 3 * k).astype(np.float32) for k in range(n)]
+    for m in maps:
+        m[rng.random((h, w)) < 0.25] = np.nan
+    maps[0][:3] = np.nan
+    for m in maps:
+        m[5, :7] = np.nan                     # an all-NaN run
+    offsets = [3.0 * k + 0.1234567 for k in range(n)]
+    return maps, offsets
+
+
+@pytest.mark.parametrize("n", [2, 3, 5])
+def test_port_matches_reference_function(n):
+    from oracle import fusion_oracle as F
+    if F.reference_average_if_close() is None:
+        pytest.skip("/root/reference not present")
+    maps, offsets = _maps(n, seed=n)
+    for thr in (1, 3):
+        assert same(F.merge_port(maps, offsets, "average_if_close", thr), F.merge_ref(maps, offsets, thr))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,op", [(2, "average_if_close"), (3, "average_if_close"), (4, "np.nanmedian"), (3, "np.nanmean"),
+                                  (5, "np.nanmin"), (2, "np.nanmax")])
+def test_gpu_merge_matches_port(engine, n, op):
+    from oracle import fusion_oracle as F
+    maps, offsets = _maps(n, seed=10 + n)
+    got = engine.merge_n(maps, offsets, op, threshold=3)
+    want = F.merge_port(maps, offsets, op, 3)
+    assert same(got, want), "%d px differ" % int((~((got == want) | (np.isnan(got) & np.isnan(want)))).sum())
+
+
+@pytest.mark.gpu
+def test_gpu_merge_dropin_files(engine, tmp_path):
+    from oracle import fusion_oracle as F
+    from s2p_b200 import fusion, rasterio_compat as rio
+    maps, offsets = _maps(2, seed=77)
+    paths = []
+    for k, m in enumerate(maps):
+        p = str(tmp_path / ("height_map_%d.tif" % k))
+        rio.write_float_tiff(p, m)
+        paths.append(p)
+    out = str(tmp_path / "height_map.tif")
+    fusion.merge_n(out, paths, offsets, averaging="average_if_close", threshold=3)
+    assert same(rio.read_band(out), F.merge_port(maps, offsets, "average_if_close", 3))
