@@ -126,6 +126,9 @@ int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh,
 int s2pb_merge_n(s2pb_ctx *ctx, const float *const *inputs, const double *offsets, int n, int w, int h,
                  int op, double threshold, float *out);
 
+/* masking.erosion (s2p/masking.py:87-97 = `morsi diskR erosion`, c/morsi.c:54-66,280-298) on a 0/1 mask */
+int s2pb_erode_mask(s2pb_ctx *ctx, const uint8_t *in, uint8_t *out, int w, int h, float radius);
+
 /* ---- stage-level entry points (host buffers; used by the parity tests) ----- */
 /* census_tools.cc:127-153.  codes: w*h uint64, first neighbour in the top bit. */
 int s2pb_census(s2pb_ctx *ctx, const float *img, int w, int h, int win, uint64_t *codes);

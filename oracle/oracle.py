@@ -258,3 +258,19 @@ def run_ref_homography(src, H, w, h, binary="homography_ref", workdir=None):
 
 def have_ref_homography():
     return os.access(os.path.join(REF_DIR, "homography_ref"), os.X_OK)
+
+
+def ref_disk_erosion(mask, radius=2.0):
+    """The reference's `morsi diskR erosion` (oracle/_ref/libmorsi_ref.so = c/morsi.c compiled in place)."""
+    L = ctypes.CDLL(os.path.join(REF_DIR, "libmorsi_ref.so"))
+    x = _f32(mask)
+    h, w = x.shape
+    y = np.empty_like(x)
+    rc = L.s2pb_ref_disk_erosion(_p(y), _p(x), w, h, ctypes.c_float(radius))
+    if rc:
+        raise ValueError("radius must be > 1")
+    return y
+
+
+def have_ref_morsi():
+    return os.path.exists(os.path.join(REF_DIR, "libmorsi_ref.so"))

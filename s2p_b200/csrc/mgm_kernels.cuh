@@ -375,4 +375,23 @@ __global__ void rejection_mask_kernel(const float *__restrict__ disp, const floa
     mask[idx] = (isfinite(d) && isfinite(im1[idx]) && isfinite(r)) ? 1 : 0;
 }
 
+
+// masking.erosion (s2p/masking.py:87-97 -> `morsi diskR erosion`, c/morsi.c:54-66,280-298): minimum over the
+// discrete disk {(i,j) : hypot(i,j) < R}; samples outside the image are NaN for the reference's fmin, i.e. ignored.
+__global__ void erode_mask_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h, float radius)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int r = (int)radius + 1;
+    unsigned v = 255;
+    for (int i = -r; i <= r; i++)
+        for (int j = -r; j <= r; j++) {
+            if (!(hypot((double)i, (double)j) < (double)radius)) continue;
+            int xx = x + i, yy = y + j;
+            if (xx < 0 || xx >= w || yy < 0 || yy >= h) continue;
+            v = min(v, (unsigned)in[(size_t)yy * w + xx]);
+        }
+    out[(size_t)y * w + x] = (uint8_t)v;
+}
+
 }  // namespace s2pb

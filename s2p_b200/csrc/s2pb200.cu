@@ -1123,6 +1123,25 @@ extern "C" int s2pb_remove_small_cc(s2pb_ctx *ctx, const float *in, float *out, 
     return S2PB_OK;
 }
 
+extern "C" int s2pb_erode_mask(s2pb_ctx *ctx, const uint8_t *in, uint8_t *out, int w, int h, float radius)
+{
+    if (!ctx || !in || !out || w < 1 || h < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    if (!(radius > 1.f) || radius > 64.f) return fail(S2PB_ERR_ARG, "disk radius must be in (1, 64]");   // build_disk, c/morsi.c:282
+    CK(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)w * h;
+    DevBuf a, b;
+    ALLOC(a, npix); ALLOC(b, npix);
+    cudaStream_t st = ctx->slots[0].stream;
+    CK(cudaMemcpyAsync(a.p, in, npix, cudaMemcpyHostToDevice, st));
+    dim3 b2(32, 8);
+    erode_mask_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(a.as<uint8_t>(), b.as<uint8_t>(), w, h, radius);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, b.p, npix, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
 extern "C" int s2pb_rejection_mask(s2pb_ctx *ctx, const float *disp, const float *im1, const float *im2, int w, int h, uint8_t *mask)
 {
     if (!ctx || !disp || !im1 || !im2 || !mask || w < 1 || h < 1) return fail(S2PB_ERR_ARG, "bad argument");

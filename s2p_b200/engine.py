@@ -153,6 +153,15 @@ class Engine:
         _lib.check(self._L.s2pb_merge_n(self._ctx, ptrs, offs, n, w, h, self.FUSION_OPS[averaging], float(threshold), _fp(out)))
         return out
 
+    def erode_mask(self, mask, radius=2):
+        """`morsi diskR erosion` of a 0/1 mask (s2p/masking.py:87-97)."""
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        h, w = m.shape
+        out = np.empty_like(m)
+        u8 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+        _lib.check(self._L.s2pb_erode_mask(self._ctx, u8(m), u8(out), w, h, float(radius)))
+        return out
+
     # ------------------------------------------------------------------ stages (parity tests)
     def census(self, img, win=5):
         img = _f32(img)

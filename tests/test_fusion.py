@@ -53,3 +53,24 @@ def test_gpu_merge_dropin_files(engine, tmp_path):
     out = str(tmp_path / "height_map.tif")
     fusion.merge_n(out, paths, offsets, averaging="average_if_close", threshold=3)
     assert same(rio.read_band(out), F.merge_port(maps, offsets, "average_if_close", 3))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radius", [2, 3, 5])
+def test_gpu_mask_erosion_matches_reference(engine, oracle, radius, tmp_path):
+    """masking.erosion = `morsi diskR erosion` (c/morsi.c compiled in place as oracle/_ref/libmorsi_ref.so)."""
+    if not oracle.have_ref_morsi():
+        pytest.skip("oracle/_ref/libmorsi_ref.so not built")
+    rng = np.random.default_rng(radius)
+    m = (rng.random((61, 83)) > 0.15).astype(np.uint8)
+    want = oracle.ref_disk_erosion(m.astype(np.float32), radius).astype(np.uint8)
+    assert np.array_equal(engine.erode_mask(m, radius), want)
+    if radius == 2:       # file-level drop-in (s2p/masking.py:87-97)
+        from s2p_b200 import masking, rasterio_compat as rio
+        p = str(tmp_path / "rectified_mask.png")
+        rio.write_mask_png(p, m)
+        masking.erosion(p, p, 2)
+        assert np.array_equal(rio.read_band(p).astype(np.uint8), want)
+        rio.write_mask_png(p, m)
+        masking.erosion(p, p, 1)                      # below 2: untouched, as in the reference
+        assert np.array_equal(rio.read_band(p).astype(np.uint8), m)
