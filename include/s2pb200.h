@@ -126,6 +126,22 @@ int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh,
 int s2pb_merge_n(s2pb_ctx *ctx, const float *const *inputs, const double *offsets, int n, int w, int h,
                  int op, double threshold, float *out);
 
+/* ---- triangulation (a "next" row of SURVEY.md section 8f) --------------------- */
+/* Rational polynomial camera model: the reference's `struct rpc` (c/rpc.h:14-32) field for field, which is also
+ * the layout of s2p.triangulation.RPCStruct (s2p/triangulation.py:23-40). */
+typedef struct s2pb_rpc {
+    double numx[20], denx[20], numy[20], deny[20], scale[3], offset[3];
+    double inumx[20], idenx[20], inumy[20], ideny[20], iscale[3], ioffset[3];
+    double dmval[4], imval[4];
+    double delta;
+} s2pb_rpc;
+/* Same argument list as lib/disp_to_h.so's disp_to_lonlatalt (c/disp_to_h.c:70-76), which
+ * s2p.triangulation.disp_to_xyz calls through ctypes (s2p/triangulation.py:118-143), plus the context. */
+int s2pb_disp_to_lonlatalt(s2pb_ctx *ctx, double *lonlatalt, float *err, const float *dispx, const float *dispy,
+                           const float *msk, int nx, int ny, const float *msk_orig, int w, int h,
+                           const double ha[9], const double hb[9], const s2pb_rpc *rpca, const s2pb_rpc *rpcb,
+                           const float orig_img_bounding_box[4]);
+
 /* masking.erosion (s2p/masking.py:87-97 = `morsi diskR erosion`, c/morsi.c:54-66,280-298) on a 0/1 mask */
 int s2pb_erode_mask(s2pb_ctx *ctx, const uint8_t *in, uint8_t *out, int w, int h, float radius);
 

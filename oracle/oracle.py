@@ -274,3 +274,26 @@ def ref_disk_erosion(mask, radius=2.0):
 
 def have_ref_morsi():
     return os.path.exists(os.path.join(REF_DIR, "libmorsi_ref.so"))
+
+
+def ref_disp_to_lonlatalt(disp, mask_rect, mask_orig, H1, H2, rpc1, rpc2, img_bbx):
+    """The reference's lib/disp_to_h.so entry point (oracle/_ref/libdisp_to_h_ref.so = c/disp_to_h.c + c/rpc.c
+    compiled in place), called the way s2p/triangulation.py:118-143 calls it."""
+    L = ctypes.CDLL(os.path.join(REF_DIR, "libdisp_to_h_ref.so"))
+    dispx = _f32(disp)
+    h, w = dispx.shape
+    dispy = np.zeros((h, w), np.float32)
+    msk, mo = _f32(mask_rect), _f32(mask_orig)
+    hh, ww = mo.shape
+    out = np.zeros((h, w, 3), np.float64)
+    err = np.zeros((h, w), np.float32)
+    Ha = np.ascontiguousarray(np.asarray(H1, np.float64).reshape(9))
+    Hb = np.ascontiguousarray(np.asarray(H2, np.float64).reshape(9))
+    bb = np.ascontiguousarray(np.asarray(img_bbx, np.float32).reshape(4))
+    L.disp_to_lonlatalt(_p(out, ctypes.c_double), _p(err), _p(dispx), _p(dispy), _p(msk), w, h, _p(mo), ww, hh,
+                        _p(Ha, ctypes.c_double), _p(Hb, ctypes.c_double), ctypes.byref(rpc1), ctypes.byref(rpc2), _p(bb))
+    return out, err
+
+
+def have_ref_triangulation():
+    return os.path.exists(os.path.join(REF_DIR, "libdisp_to_h_ref.so"))

@@ -9,6 +9,7 @@
 #include "multiscale_kernels.cuh"
 #include "homography_kernels.cuh"
 #include "fusion_kernels.cuh"
+#include "triangulation_kernels.cuh"
 #include "agg_dispatch.h"
 
 #include <chrono>
@@ -1331,6 +1332,58 @@ extern "C" int s2pb_merge_n(s2pb_ctx *ctx, const float *const *inputs, const dou
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, o.p, npix * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+// ------------------------------------------------------------------ triangulation (section 8f)
+
+static_assert(sizeof(s2pb_rpc) == sizeof(RpcModel), "s2pb_rpc must have the layout of the reference's struct rpc");
+
+// Same argument list as the reference's ctypes entry point disp_to_lonlatalt (c/disp_to_h.c:70-76), plus the context.
+extern "C" int s2pb_disp_to_lonlatalt(s2pb_ctx *ctx, double *lonlatalt, float *err, const float *dispx, const float *dispy,
+                                      const float *msk, int nx, int ny, const float *msk_orig, int w, int h, const double ha[9],
+                                      const double hb[9], const s2pb_rpc *rpca, const s2pb_rpc *rpcb, const float bbox[4])
+{
+    if (!ctx || !lonlatalt || !err || !dispx || !dispy || !msk || !msk_orig || !ha || !hb || !rpca || !rpcb || !bbox || nx < 1 ||
+        ny < 1 || w < 1 || h < 1)
+        return fail(S2PB_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)nx * ny, nm = (size_t)w * h;
+    cudaStream_t st = ctx->slots[0].stream;
+    DevBuf d_dx, d_dy, d_m, d_mo, d_rpc, d_out, d_err;
+    ALLOC(d_dx, npix * 4); ALLOC(d_dy, npix * 4); ALLOC(d_m, npix * 4); ALLOC(d_mo, nm * 4);
+    ALLOC(d_rpc, 2 * sizeof(RpcModel)); ALLOC(d_out, npix * 24); ALLOC(d_err, npix * 4);
+    CK(cudaMemcpyAsync(d_dx.p, dispx, npix * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_dy.p, dispy, npix * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_m.p, msk, npix * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_mo.p, msk_orig, nm * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_rpc.p, rpca, sizeof(RpcModel), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((char *)d_rpc.p + sizeof(RpcModel), rpcb, sizeof(RpcModel), cudaMemcpyHostToDevice, st));
+    TriParams P;
+    memset(&P, 0, sizeof P);
+    P.dispx = d_dx.as<float>(); P.dispy = d_dy.as<float>(); P.msk = d_m.as<float>(); P.msk_orig = d_mo.as<float>();
+    P.nx = nx; P.ny = ny; P.w = w; P.h = h;
+    {   // invert_homography, c/disp_to_h.c:26-42
+        const double *m[2] = {ha, hb};
+        double *o[2] = {P.ha_inv, P.hb_inv};
+        for (int k = 0; k < 2; k++) {
+            const double *i = m[k];
+            const double det = i[0] * i[4] * i[8] + i[2] * i[3] * i[7] + i[1] * i[5] * i[6] - i[2] * i[4] * i[6] - i[1] * i[3] * i[8] - i[0] * i[5] * i[7];
+            o[k][0] = (i[4] * i[8] - i[5] * i[7]) / det; o[k][1] = (i[2] * i[7] - i[1] * i[8]) / det; o[k][2] = (i[1] * i[5] - i[2] * i[4]) / det;
+            o[k][3] = (i[5] * i[6] - i[3] * i[8]) / det; o[k][4] = (i[0] * i[8] - i[2] * i[6]) / det; o[k][5] = (i[2] * i[3] - i[0] * i[5]) / det;
+            o[k][6] = (i[3] * i[7] - i[4] * i[6]) / det; o[k][7] = (i[1] * i[6] - i[0] * i[7]) / det; o[k][8] = (i[0] * i[4] - i[1] * i[3]) / det;
+        }
+    }
+    P.rpca = d_rpc.as<RpcModel>(); P.rpcb = d_rpc.as<RpcModel>() + 1;
+    P.col_min = bbox[0]; P.col_max = bbox[1]; P.row_min = bbox[2]; P.row_max = bbox[3];
+    P.lonlatalt = d_out.as<double>(); P.err = d_err.as<float>();
+    dim3 b2(32, 8);
+    triangulate_kernel<<<grid2d(nx, ny, b2), b2, 0, st>>>(P);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(lonlatalt, d_out.p, npix * 24, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(err, d_err.p, npix * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return S2PB_OK;
 }

@@ -26,8 +26,9 @@ def rectify_pair(im1, im2, rpc1, rpc2, x, y, w, h, out1, out2, A=None, sift_matc
 def install():
     """Patch an importable s2p: both boundaries (matcher and warp) and the two "next" rows already served
     (mask erosion, n-view merge) go to the B200 engine."""
-    from . import block_matching, fusion, masking
+    from . import block_matching, fusion, masking, triangulation
     common.install()
     block_matching.install()
     masking.install()
     fusion.install()
+    triangulation.install()
