@@ -32,35 +32,60 @@ __global__ void transpose_kernel(const float *__restrict__ in, int w, int h, flo
         if (ox < h && oy0 + k < w) out[(size_t)(oy0 + k) * h + ox] = t[threadIdx.x][k];
 }
 
-// applySpline (Splines.cpp:234-270) down every column of a w x h image, one thread per column:
-// scale by lambda, then for each of the two poles a forward and a backward recursion whose start values
-// come from initForward (:315-340, a full-length weighted sum) and initBackward (:375-384).
+// applySpline (Splines.cpp:234-270) down every column of a w x h image, one thread per column (coalesced across
+// the warp): scale by lambda, then for each of the two poles a forward and a backward recursion whose start values
+// come from initForward (:315-340, a full-length weighted sum) and initBackward (:375-384).  The recursions are
+// sequential in k, exactly as in the reference; rows are moved in register blocks of kSplineBlk so that the
+// global-memory latency is paid once per block instead of once per row.
+constexpr int kSplineBlk = 16;
 __global__ void spline_columns_kernel(float *__restrict__ a, int w, int h, float lambda, double z0, double z1)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
     float *v = a + x;
     const size_t st = (size_t)w;
-    for (int k = 0; k < h; k++) v[k * st] *= lambda;
+    float buf[kSplineBlk];
     for (int n = 0; n < 2; n++) {
         const double pz = n == 0 ? z0 : z1;
         const float zn = (float)pz;
-        // initForward
+        // every applySpline call scales the line by lambda first; the second pole sees the line already scaled
+        const float scale = n == 0 ? lambda : 1.f;
+        // initForward: sum = v[0] + z^(h-1) v[h-1] + sum_k (z^k + z^(2h-2-k)) v[k]
         double zk = pz, iz = 1.0 / pz, z2k = pow(pz, (double)(h - 1));
-        float sum = v[0] + (float)z2k * v[(size_t)(h - 1) * st];
+        float sum = v[0] * scale + (float)z2k * (v[(size_t)(h - 1) * st] * scale);
         z2k = z2k * z2k * iz;
-        for (int k = 1; k < h - 1; k++) {
-            sum = fmaf((float)(zk + z2k), v[k * st], sum);
-            zk *= pz;
-            z2k *= iz;
+        for (int k0 = 1; k0 < h - 1; k0 += kSplineBlk) {
+            const int m = min(kSplineBlk, h - 1 - k0);
+#pragma unroll
+            for (int q = 0; q < kSplineBlk; q++) if (q < m) buf[q] = v[(size_t)(k0 + q) * st] * scale;
+#pragma unroll
+            for (int q = 0; q < kSplineBlk; q++)
+                if (q < m) { sum = fmaf((float)(zk + z2k), buf[q], sum); zk *= pz; z2k *= iz; }
         }
         sum = __fdiv_rn(sum, (float)(1.0 - zk * zk));
+        // forward recursion (also applies the scale of the first pole in place)
         v[0] = sum;
-        for (int k = 1; k < h; k++) { sum = fmaf(zn, sum, v[k * st]); v[k * st] = sum; }
-        // initBackward
+        for (int k0 = 1; k0 < h; k0 += kSplineBlk) {
+            const int m = min(kSplineBlk, h - k0);
+#pragma unroll
+            for (int q = 0; q < kSplineBlk; q++) if (q < m) buf[q] = v[(size_t)(k0 + q) * st] * scale;
+#pragma unroll
+            for (int q = 0; q < kSplineBlk; q++) if (q < m) { sum = fmaf(zn, sum, buf[q]); buf[q] = sum; }
+#pragma unroll
+            for (int q = 0; q < kSplineBlk; q++) if (q < m) v[(size_t)(k0 + q) * st] = buf[q];
+        }
+        // initBackward + backward recursion
         sum = (float)(pz / (pz * pz - 1.0)) * fmaf((float)pz, v[(size_t)(h - 2) * st], v[(size_t)(h - 1) * st]);
         v[(size_t)(h - 1) * st] = sum;
-        for (int k = h - 2; k >= 0; k--) { sum = zn * (sum - v[k * st]); v[k * st] = sum; }
+        for (int k0 = h - 2; k0 >= 0; k0 -= kSplineBlk) {
+            const int m = min(kSplineBlk, k0 + 1);
+#pragma unroll
+            for (int q = 0; q < kSplineBlk; q++) if (q < m) buf[q] = v[(size_t)(k0 - q) * st];
+#pragma unroll
+            for (int q = 0; q < kSplineBlk; q++) if (q < m) { sum = zn * (sum - buf[q]); buf[q] = sum; }
+#pragma unroll
+            for (int q = 0; q < kSplineBlk; q++) if (q < m) v[(size_t)(k0 - q) * st] = buf[q];
+        }
     }
 }
 

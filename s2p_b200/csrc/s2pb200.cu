@@ -1239,9 +1239,9 @@ static int map_image(s2pb_ctx *ctx, cudaStream_t st, const float *d_src, int w, 
     nan_to_zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp.as<float>(), n);
     dim3 bt(32, 8);
     transpose_kernel<<<dim3((tw + 31) / 32, (th + 31) / 32), bt, 0, st>>>(tmp.as<float>(), tw, th, scratch.as<float>());
-    spline_columns_kernel<<<(th + 127) / 128, 128, 0, st>>>(scratch.as<float>(), th, tw, lambda, z0, z1);      // rows of the image
+    spline_columns_kernel<<<(th + 31) / 32, 32, 0, st>>>(scratch.as<float>(), th, tw, lambda, z0, z1);      // rows of the image
     transpose_kernel<<<dim3((th + 31) / 32, (tw + 31) / 32), bt, 0, st>>>(scratch.as<float>(), th, tw, tmp.as<float>());
-    spline_columns_kernel<<<(tw + 127) / 128, 128, 0, st>>>(tmp.as<float>(), tw, th, lambda, z0, z1);
+    spline_columns_kernel<<<(tw + 31) / 32, 32, 0, st>>>(tmp.as<float>(), tw, th, lambda, z0, z1);
     Mat9 Hi;
     invert33(useZ ? matZ : M, Hi.m);
     spline_warp_kernel<<<grid2d(ow, oh, b2), b2, 0, st>>>(tmp.as<float>(), tw, th, Hi, d_out, ow, oh);
