@@ -131,16 +131,33 @@ __global__ void cc_init_kernel(const float *__restrict__ in, int n, int *__restr
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { lab[i] = isnan(in[i]) ? -1 : i; area[i] = 0; }
 }
+// horizontal links: one thread per row walks it left to right and labels every run of linked pixels with the
+// index of the run's first pixel -- no atomics.  (The reference makes no horizontal link in the last row.)
+__global__ void cc_rows_kernel(const float *__restrict__ in, int w, int h, float thr, int *lab)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= h - 1) return;
+    const float *row = in + (size_t)j * w;
+    int *l = lab + (size_t)j * w;
+    int start = -1;
+    float prev = 0.f;
+    for (int i = 0; i < w; i++) {
+        const float a = row[i];
+        if (isnan(a)) { start = -1; continue; }              // lab stays -1 (cc_init)
+        // link (i-1, i) exists when i-1 < w-1 (always), both valid and close
+        if (start >= 0 && fabs((double)(prev - a)) < (double)thr) l[i] = j * w + start;
+        else { start = i; }
+        prev = a;
+    }
+}
+// vertical links (none in the last column, as in the reference): union of the two runs' roots
 __global__ void cc_link_kernel(const float *__restrict__ in, int w, int h, float thr, int *lab)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= w - 1 || j >= h - 1) return;
-    int p0 = j * w + i;
-    if (lab[p0] < 0) return;
-    float a = in[p0];
-    int p1 = p0 + 1, p2 = p0 + w;
-    if (lab[p1] >= 0 && fabs((double)(a - in[p1])) < (double)thr) uf_union(lab, p0, p1);
-    if (lab[p2] >= 0 && fabs((double)(a - in[p2])) < (double)thr) uf_union(lab, p0, p2);
+    int p0 = j * w + i, p2 = p0 + w;
+    if (lab[p0] < 0 || lab[p2] < 0) return;
+    if (fabs((double)(in[p0] - in[p2])) < (double)thr) uf_union(lab, p0, p2);
 }
 __global__ void cc_area_kernel(int n, int *lab, int *area)
 {

@@ -89,9 +89,27 @@ struct s2pb_ctx {
     int *scratch_flag = nullptr;   // pinned + mapped: device -> host one-word answers
     int *d_scratch = nullptr;      // 64 words of device memory (hull accumulators of mgm_multi)
     long long launches = 0;
+    // scratch pool of the warp / stage entry points: device buffers are kept between calls
+    struct PoolBuf { void *p; size_t bytes; bool used; };
+    std::vector<PoolBuf> pool;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// smallest free pooled buffer that is large enough, else a new allocation (nullptr when out of memory)
+static void *pool_take(s2pb_ctx *ctx, size_t bytes)
+{
+    int best = -1;
+    for (int i = 0; i < (int)ctx->pool.size(); i++)
+        if (!ctx->pool[i].used && ctx->pool[i].bytes >= bytes && (best < 0 || ctx->pool[i].bytes < ctx->pool[best].bytes)) best = i;
+    if (best >= 0) { ctx->pool[best].used = true; return ctx->pool[best].p; }
+    void *p = nullptr;
+    size_t want = align_up(bytes ? bytes : 1, (size_t)1 << 20);
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->pool.push_back({p, want, true});
+    return p;
+}
+static void pool_release_all(s2pb_ctx *ctx) { for (auto &b : ctx->pool) b.used = false; }
 
 static int lpl_for(int D)
 {
@@ -250,6 +268,7 @@ extern "C" void s2pb_destroy(s2pb_ctx *ctx)
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    for (auto &b : ctx->pool) cudaFree(b.p);
     if (ctx->abort_flag) cudaFreeHost(ctx->abort_flag);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     delete ctx;
@@ -478,10 +497,11 @@ static int launch_remove_small_cc(s2pb_ctx *ctx, const float *in, float *out, in
     int n = w * h;
     dim3 b2(32, 8);
     cc_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(in, n, lab, area);
+    cc_rows_kernel<<<(h + 63) / 64, 64, 0, st>>>(in, w, h, 5.f, lab);
     cc_link_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(in, w, h, 5.f, lab);
     cc_area_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, lab, area);
     cc_filter_kernel<<<(n + 255) / 256, 256, 0, st>>>(in, n, lab, area, minarea, out);
-    ctx->launches += 4;
+    ctx->launches += 5;
     CK(cudaGetLastError());
     return S2PB_OK;
 }
@@ -1189,6 +1209,8 @@ static float min_zoom_out(const double m[9], size_t w, size_t h)
     return std::fmin(1.f, r);
 }
 
+struct PoolRef { void *p = nullptr; template <class T> T *as() { return (T *)p; } };
+
 // mapImage (Homography.cpp:50-168) on device images; recursive through the anti-aliasing branch.
 static int map_image(s2pb_ctx *ctx, cudaStream_t st, const float *d_src, int w, int h, const double M[9], float *d_out, int ow, int oh,
                      bool use_aa, int depth)
@@ -1198,7 +1220,8 @@ static int map_image(s2pb_ctx *ctx, cudaStream_t st, const float *d_src, int w, 
     const float zoomOut = use_aa ? min_zoom_out(M, (size_t)w, (size_t)h) : 1.f;
     const bool useZ = zoomOut < 1.f;
     double matZ[9] = {0};
-    DevBuf tmp, scratch;
+    PoolRef tmp, scratch;
+#define POOL(buf, n) do { (buf).p = pool_take(ctx, (n)); if (!(buf).p) return fail(S2PB_ERR_NOMEM, "cudaMalloc of %zu bytes failed", (size_t)(n)); } while (0)
     int tw = w, th = h;
     if (useZ) {
         const float zoomIn = 1.0f / zoomOut;
@@ -1207,8 +1230,8 @@ static int map_image(s2pb_ctx *ctx, cudaStream_t st, const float *d_src, int w, 
         if (tw < 1 || th < 1 || (size_t)tw * th > ((size_t)1 << 31)) return fail(S2PB_ERR_ARG, "homography: degenerate zoom %g", (double)zoomIn);
         for (int k = 0; k < 6; k++) matZ[k] = zoomIn * M[k];
         for (int k = 6; k < 9; k++) matZ[k] = M[k];
-        ALLOC(tmp, (size_t)tw * th * 4);
-        ALLOC(scratch, (size_t)tw * th * 4);
+        POOL(tmp, (size_t)tw * th * 4);
+        POOL(scratch, (size_t)tw * th * 4);
         int rc = map_image(ctx, st, d_src, w, h, matZ, tmp.as<float>(), tw, th, true, depth + 1);
         if (rc != S2PB_OK) return rc;
         // Gaussian of sigma = 0.8 sqrt(zoomIn^2 - 1) (Homography.cpp:101-102, LibImages.cpp:506-687)
@@ -1228,8 +1251,8 @@ static int map_image(s2pb_ctx *ctx, cudaStream_t st, const float *d_src, int w, 
         ctx->launches += 2;
         matZ[0] = zoomOut; matZ[1] = 0; matZ[2] = 0; matZ[3] = 0; matZ[4] = zoomOut; matZ[5] = 0; matZ[6] = 0; matZ[7] = 0; matZ[8] = 1;
     } else {
-        ALLOC(tmp, (size_t)w * h * 4);
-        ALLOC(scratch, (size_t)w * h * 4);
+        POOL(tmp, (size_t)w * h * 4);
+        POOL(scratch, (size_t)w * h * 4);
         CK(cudaMemcpyAsync(tmp.p, d_src, (size_t)w * h * 4, cudaMemcpyDeviceToDevice, st));
     }
     // prepareSpline (Splines.cpp:26-121): NaN -> 0, 2-pole prefilter along rows, then along columns
@@ -1253,8 +1276,8 @@ static int map_image(s2pb_ctx *ctx, cudaStream_t st, const float *d_src, int w, 
         ctx->launches++;
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));     // the scratch buffers of this level are released on return
-    return S2PB_OK;
+#undef POOL
+    return S2PB_OK;     // buffers stay taken until the whole warp is done (stream order protects them)
 }
 
 // `homography im -h "..." out w h` (3rdparty/homography/main.cpp:65-177) from memory to memory
@@ -1292,14 +1315,15 @@ extern "C" int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh, 
     double Hc[9];
     for (int r = 0; r < 3; r++) for (int q = 0; q < 3; q++) Hc[3 * r + q] = H[3 * r] * T[q] + H[3 * r + 1] * T[3 + q] + H[3 * r + 2] * T[6 + q];
     cudaStream_t st = ctx->slots[0].stream;
-    DevBuf roi, out;
-    ALLOC(roi, (size_t)w * h * 4);
-    ALLOC(out, (size_t)dw * dh * 4);
-    CK(cudaMemcpy2DAsync(roi.p, (size_t)w * 4, src + (size_t)y * sw + x, (size_t)sw * 4, (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice, st));
-    int rc = map_image(ctx, st, roi.as<float>(), w, h, Hc, out.as<float>(), dw, dh, true, 0);
-    if (rc != S2PB_OK) return rc;
-    CK(cudaMemcpyAsync(dst, out.p, (size_t)dw * dh * 4, cudaMemcpyDeviceToHost, st));
+    pool_release_all(ctx);
+    float *roi = (float *)pool_take(ctx, (size_t)w * h * 4), *out = (float *)pool_take(ctx, (size_t)dw * dh * 4);
+    if (!roi || !out) { pool_release_all(ctx); return fail(S2PB_ERR_NOMEM, "cudaMalloc failed for the warp buffers"); }
+    CK(cudaMemcpy2DAsync(roi, (size_t)w * 4, src + (size_t)y * sw + x, (size_t)sw * 4, (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice, st));
+    int rc = map_image(ctx, st, roi, w, h, Hc, out, dw, dh, true, 0);
+    if (rc != S2PB_OK) { cudaStreamSynchronize(st); pool_release_all(ctx); return rc; }
+    CK(cudaMemcpyAsync(dst, out, (size_t)dw * dh * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    pool_release_all(ctx);
     return S2PB_OK;
 }
 
