@@ -208,3 +208,38 @@ def test_mgm_multi(engine, oracle, shape, dmin, dmax, nanb, seed, kw):
         frac_nan_diff = (np.isnan(d) != np.isnan(out["disp"])).mean()
         big = (np.abs(d[both] - out["disp"][both]) > SUBPIX_TOL).mean() if both.any() else 0.0
         assert frac_nan_diff < 2e-3 and big < 2e-3, (frac_nan_diff, big, nmismatch(out["disp"], d))
+
+
+@pytest.mark.parametrize("shape,dmin,dmax", [((2, 2), -1, 1), ((3, 9), -2, 3), ((9, 3), -4, 1), ((17, 5), 0, 6), ((6, 40), -20, 20),
+                                             ((33, 34), -3, 2), ((150, 7), -5, 5)])
+def test_tiny_and_thin_tiles(engine, oracle, shape, dmin, dmax):
+    """Shapes smaller than a band (16 scanlines), than the cp.async pipeline (8 pixels) or than the census window."""
+    from s2p_b200.engine import default_params
+    h, w = shape
+    rng = np.random.default_rng(h * 100 + w)
+    ref = rng.integers(0, 4096, (h, w)).astype(np.float32)
+    sec = np.roll(ref, 1, axis=1) + rng.normal(0, 20, (h, w)).astype(np.float32)
+    out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm"), want_right=True)
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params())
+    assert same(out["disp"], d) and same(out["conf"], c) and same(out["disp_right"], dr)
+    assert np.array_equal(out["mask"], oracle.port.rejection_mask(d, ref, sec))
+
+
+def test_mgm_multi_batch_and_file_dropin(engine, oracle, tmp_path):
+    """algo='mgm_multi' through the batch entry point and through compute_disparity_map."""
+    from s2p_b200 import block_matching as bm, rasterio_compat as rio
+    from s2p_b200.engine import default_params
+    h, w, dmin, dmax = 110, 130, -9, 12
+    pairs = [make_pair(h, w, dmin, dmax, seed=60 + k)[:2] for k in range(3)]
+    p = default_params("mgm_multi")
+    disp, conf, mask = engine.mgm_batch([a for a, _ in pairs], [b for _, b in pairs], dmin, dmax, p)
+    for k, (a, b) in enumerate(pairs):
+        one = engine.mgm(a, b, dmin, dmax, p)
+        assert same(disp[k], one["disp"]) and same(conf[k], one["conf"]) and np.array_equal(mask[k], one["mask"])
+    im1, im2 = str(tmp_path / "a.tif"), str(tmp_path / "b.tif")
+    dpath, mpath = str(tmp_path / "d.tif"), str(tmp_path / "m.png")
+    rio.write_float_tiff(im1, pairs[0][0])
+    rio.write_float_tiff(im2, pairs[0][1])
+    bm.compute_disparity_map(im1, im2, dpath, mpath, "mgm_multi", dmin, dmax)
+    assert same(rio.read_band(dpath), disp[0])
+    assert same(rio.read_band(bm.confidence_path(dpath)), conf[0])
