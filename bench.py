@@ -9,7 +9,7 @@ A "step" = one pass of the hot path over a batch of `--tiles` synthetic rectifie
 `value`  : whole-job Mpix/s with the pairs already resident in HBM (device pointers through
            s2pb_mgm_device, CUDA-event timed on the launching streams, max over ranks).
 `e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers
-           (s2pb_mgm_batch: pinned staging, H2D, kernels, D2H every step).
+           (s2pb_mgm_batch from page-locked host buffers: H2D, kernels, D2H every step).
 `roofline`: the 8-path aggregation kernel, algorithmic bytes (12 B per voxel
            per path = 192 B per left-reference voxel for the two views) / its CUDA-event duration.
 `cpu_baseline`: the reference's own `mgm` binary (oracle/_ref, built from the reference sources)
@@ -263,14 +263,23 @@ def run_ours(a, rank, world, local_rank):
     valid = float(torch.isfinite(d_disp[0]).float().mean().item())
 
     # ---- end-to-end arm: host buffers through the C ABI
-    refs = [r for r, _ in pairs]
-    secs = [s for _, s in pairs]
+    # host buffers are page-locked (torch pinned tensors viewed as numpy): the library DMAs from / to them directly
+    keep = []
+
+    def pinned(arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+    refs = [pinned(r) for r, _ in pairs]
+    secs = [pinned(s) for _, s in pairs]
+    outs = ([pinned(np.empty((H, W), np.float32)) for _ in pairs], [pinned(np.empty((H, W), np.float32)) for _ in pairs],
+            [pinned(np.empty((H, W), np.uint8)) for _ in pairs])
     for _ in range(max(1, min(3, a.warmup))):
-        eng.mgm_batch(refs, secs, a.dmin, a.dmax, p)
+        eng.mgm_batch(refs, secs, a.dmin, a.dmax, p, out=outs)
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        out = eng.mgm_batch(refs, secs, a.dmin, a.dmax, p)
+        out = eng.mgm_batch(refs, secs, a.dmin, a.dmax, p, out=outs)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = pix_step * a.steps / e2e_s / 1e6
@@ -339,7 +348,7 @@ def run_ours(a, rank, world, local_rank):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config(a, world), "gvoxel_per_s": value * D / 1e3,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "timer": "host wall clock around the synchronised region (staging memcpys included), max over ranks",
+                    "timer": "host wall clock around the synchronised region, max over ranks; page-locked host buffers on both sides",
                     "gvoxel_per_s": e2e * D / 1e3},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "valid_fraction_tile0": valid,

@@ -80,6 +80,7 @@ struct Slot {
     cudaEvent_t ev[S2PB_T_COUNT + 1] = {};
     cudaEvent_t done = nullptr;
     bool timed = false;
+    bool direct_out = false;      // the last host-API call wrote its results straight into the caller's pinned buffers
 };
 struct s2pb_ctx {
     int device = 0;
@@ -856,32 +857,48 @@ extern "C" int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, cons
     return S2PB_OK;
 }
 
+// true when `p` is page-locked host memory known to CUDA (cudaHostAlloc / cudaHostRegister, e.g. a torch pinned
+// tensor): such buffers are used for the DMA directly instead of being staged through the slot's pinned block
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 // stage the inputs of one tile through pinned memory and enqueue everything on the slot's stream
 static int mgm_host_enqueue(s2pb_ctx *ctx, Slot &s, const float *im1, const float *im2, int w, int h, int dmin, int dmax,
-                            const s2pb_mgm_params *p, bool want_mask, bool want_right)
+                            const s2pb_mgm_params *p, bool want_mask, bool want_right,
+                            float *o_disp = nullptr, float *o_conf = nullptr, uint8_t *o_mask = nullptr)
 {
     size_t npix = (size_t)w * h;
     int rc = slot_host_ensure(s, npix);
     if (rc != S2PB_OK) return rc;
-    // copy into the pinned staging block, noticing no-data pixels of the secondary image on the way
-    memcpy(s.h_in[0], im1, npix * 4);
+    // copy into the pinned staging block (unless the caller's buffers are page-locked already), noticing no-data
+    // pixels of the secondary image on the way
+    const float *src1 = im1, *src2 = im2;
+    if (!is_pinned_host(im1)) { memcpy(s.h_in[0], im1, npix * 4); src1 = s.h_in[0]; }
     bool sec_nodata = false;
     {
+        const bool pinned2 = is_pinned_host(im2);
         float *dst = s.h_in[1];
         unsigned acc = 0;
-        for (size_t i = 0; i < npix; i++) { float v = im2[i]; dst[i] = v; acc |= (unsigned)(v != v); }
+        if (pinned2) { for (size_t i = 0; i < npix; i++) { float v = im2[i]; acc |= (unsigned)(v != v); } }
+        else { for (size_t i = 0; i < npix; i++) { float v = im2[i]; dst[i] = v; acc |= (unsigned)(v != v); } src2 = dst; }
         sec_nodata = acc != 0;
     }
     rc = slot_io_ensure(s, npix);
     if (rc != S2PB_OK) return rc;
-    CK(cudaMemcpyAsync(s.d_in[0], s.h_in[0], npix * 4, cudaMemcpyHostToDevice, s.stream));
-    CK(cudaMemcpyAsync(s.d_in[1], s.h_in[1], npix * 4, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.d_in[0], src1, npix * 4, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.d_in[1], src2, npix * 4, cudaMemcpyHostToDevice, s.stream));
     rc = mgm_enqueue(ctx, s, s.d_in[0], s.d_in[1], w, h, dmin, dmax, p, s.d_disp, s.d_conf, want_mask ? s.d_mask : nullptr,
                      want_right ? s.d_dispR : nullptr, s.stream, sec_nodata ? 2 : 0);
     if (rc != S2PB_OK) return rc;
-    CK(cudaMemcpyAsync(s.h_disp, s.d_disp, npix * 4, cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaMemcpyAsync(s.h_conf, s.d_conf, npix * 4, cudaMemcpyDeviceToHost, s.stream));
-    if (want_mask) CK(cudaMemcpyAsync(s.h_mask, s.d_mask, npix, cudaMemcpyDeviceToHost, s.stream));
+    // results go straight into the caller's buffers when those are page-locked (o_* != nullptr), else to the staging block
+    s.direct_out = o_disp && o_conf && is_pinned_host(o_disp) && is_pinned_host(o_conf) && (!want_mask || (o_mask && is_pinned_host(o_mask)));
+    CK(cudaMemcpyAsync(s.direct_out ? o_disp : s.h_disp, s.d_disp, npix * 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(s.direct_out ? o_conf : s.h_conf, s.d_conf, npix * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (want_mask) CK(cudaMemcpyAsync(s.direct_out ? o_mask : s.h_mask, s.d_mask, npix, cudaMemcpyDeviceToHost, s.stream));
     if (want_right) CK(cudaMemcpyAsync(s.h_dispR, s.d_dispR, npix * 4, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaEventRecord(s.done, s.stream));
     return S2PB_OK;
@@ -895,14 +912,16 @@ extern "C" int s2pb_mgm(s2pb_ctx *ctx, const float *im1, const float *im2, int w
     if (rc != S2PB_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[0];
-    rc = mgm_host_enqueue(ctx, s, im1, im2, w, h, dmin, dmax, p, mask != nullptr, disp_right != nullptr);
+    rc = mgm_host_enqueue(ctx, s, im1, im2, w, h, dmin, dmax, p, mask != nullptr, disp_right != nullptr, disp, conf, mask);
     if (rc != S2PB_OK) return rc;
     rc = wait_with_timeout(ctx, s.stream, p->timeout_ms);
     if (rc != S2PB_OK) return rc;
     size_t npix = (size_t)w * h;
-    memcpy(disp, s.h_disp, npix * 4);
-    memcpy(conf, s.h_conf, npix * 4);
-    if (mask) memcpy(mask, s.h_mask, npix);
+    if (!s.direct_out) {
+        memcpy(disp, s.h_disp, npix * 4);
+        memcpy(conf, s.h_conf, npix * 4);
+        if (mask) memcpy(mask, s.h_mask, npix);
+    }
     if (disp_right) memcpy(disp_right, s.h_dispR, npix * 4);
     return S2PB_OK;
 }
@@ -949,9 +968,11 @@ extern "C" int s2pb_mgm_batch(s2pb_ctx *ctx, int n, const float *const *im1, con
         }
         int r = wait_with_timeout(ctx, s.stream, left);
         if (r != S2PB_OK) return r;
-        memcpy(disp[t], s.h_disp, npix * 4);
-        memcpy(conf[t], s.h_conf, npix * 4);
-        if (mask && mask[t]) memcpy(mask[t], s.h_mask, npix);
+        if (!s.direct_out) {
+            memcpy(disp[t], s.h_disp, npix * 4);
+            memcpy(conf[t], s.h_conf, npix * 4);
+            if (mask && mask[t]) memcpy(mask[t], s.h_mask, npix);
+        }
         inflight[si] = -1;
         return S2PB_OK;
     };
@@ -959,7 +980,8 @@ extern "C" int s2pb_mgm_batch(s2pb_ctx *ctx, int n, const float *const *im1, con
         int si = t % ns;
         rc = collect(si);
         if (rc != S2PB_OK) return rc;
-        rc = mgm_host_enqueue(ctx, ctx->slots[si], im1[t], im2[t], w, h, dmin, dmax, p, mask && mask[t], false);
+        rc = mgm_host_enqueue(ctx, ctx->slots[si], im1[t], im2[t], w, h, dmin, dmax, p, mask && mask[t], false, disp[t], conf[t],
+                              mask ? mask[t] : nullptr);
         if (rc != S2PB_OK) return rc;
         inflight[si] = t;
     }

@@ -84,16 +84,25 @@ class Engine:
             out["disp_right"] = right
         return out
 
-    def mgm_batch(self, refs, secs, dmin, dmax, params=None, want_mask=True):
-        """n same-shaped pairs pipelined over the context's workspaces (s2pb_reserve first for overlap)."""
+    def mgm_batch(self, refs, secs, dmin, dmax, params=None, want_mask=True, out=None):
+        """n same-shaped pairs pipelined over the context's workspaces (s2pb_reserve first for overlap).
+        ``out`` = optional (disp, conf, mask) lists of preallocated C-contiguous arrays.  Page-locked arrays (e.g.
+        numpy views of torch pinned tensors), on either side, are DMA'd directly instead of being staged."""
         p = params or default_params("mgm")
         n = len(refs)
         refs = [_f32(a) for a in refs]
         secs = [_f32(a) for a in secs]
         h, w = refs[0].shape
-        disp = [np.empty((h, w), np.float32) for _ in range(n)]
-        conf = [np.empty((h, w), np.float32) for _ in range(n)]
-        mask = [np.empty((h, w), np.uint8) for _ in range(n)] if want_mask else None
+        if out is not None:
+            disp, conf, mask = out
+            want_mask = mask is not None
+            for xs, dt in ((disp, np.float32), (conf, np.float32)) + (((mask, np.uint8),) if want_mask else ()):
+                if len(xs) != n or any(x.shape != (h, w) or x.dtype != dt or not x.flags.c_contiguous for x in xs):
+                    raise ValueError("out arrays must be %d C-contiguous (h, w) arrays of %s" % (n, np.dtype(dt).name))
+        else:
+            disp = [np.empty((h, w), np.float32) for _ in range(n)]
+            conf = [np.empty((h, w), np.float32) for _ in range(n)]
+            mask = [np.empty((h, w), np.uint8) for _ in range(n)] if want_mask else None
         arr = lambda xs: (ctypes.c_void_p * n)(*[x.ctypes.data for x in xs])
         _lib.check(self._L.s2pb_mgm_batch(self._ctx, n, arr(refs), arr(secs), w, h, int(dmin), int(dmax), ctypes.byref(p),
                                           arr(disp), arr(conf), arr(mask) if want_mask else None))

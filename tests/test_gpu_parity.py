@@ -243,3 +243,31 @@ def test_mgm_multi_batch_and_file_dropin(engine, oracle, tmp_path):
     bm.compute_disparity_map(im1, im2, dpath, mpath, "mgm_multi", dmin, dmax)
     assert same(rio.read_band(dpath), disp[0])
     assert same(rio.read_band(bm.confidence_path(dpath)), conf[0])
+
+
+@pytest.mark.gpu
+def test_batch_page_locked_buffers_match_staged(engine):
+    """Page-locked caller buffers are DMA'd directly (no staging copy); results must equal the staged path."""
+    import torch
+    from s2p_b200.engine import default_params
+    eng = engine
+    p = default_params("mgm")
+    pairs = [make_pair(70, 96, -12, 9, seed=40 + k, nan_border=0.05 if k == 1 else 0.0) for k in range(3)]
+    refs = [r for r, _, _ in pairs]
+    secs = [s for _, s, _ in pairs]
+    d0, c0, m0 = eng.mgm_batch(refs, secs, -12, 9, p)
+    keep = []
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+    outs = ([pin(np.zeros((70, 96), np.float32)) for _ in pairs], [pin(np.zeros((70, 96), np.float32)) for _ in pairs],
+            [pin(np.zeros((70, 96), np.uint8)) for _ in pairs])
+    d1, c1, m1 = eng.mgm_batch([pin(r) for r in refs], [pin(s) for s in secs], -12, 9, p, out=outs)
+    for k in range(3):
+        np.testing.assert_array_equal(d0[k], d1[k])
+        np.testing.assert_array_equal(c0[k], c1[k])
+        np.testing.assert_array_equal(m0[k], m1[k])
+    with pytest.raises(ValueError):
+        eng.mgm_batch(refs, secs, -12, 9, p, out=(outs[0][:2], outs[1], outs[2]))
