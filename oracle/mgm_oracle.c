@@ -44,6 +44,7 @@ typedef struct {
     int fix_overcount;   /* TSGM_FIX_OVERCOUNT              mgm_multiscale.cc:121      */
     int dct_shift;       /* 1: reproduce the DCT round trip of shift() (mgm_costvolume.cc:23-43);
                             0: treat a zero translation as the identity it is meant to be */
+    int cost;            /* -t : 0 census, 1 ad, 2 sd, 3 ncc, 4 btad, 5 btsd   mgm_costvolume.h:186-197 */
 } orc_params;
 
 #define ORC_INF INFINITY
@@ -56,6 +57,15 @@ static inline float fmin3_(float a, float b, float c)
     return m;
 }
 #define MINF(a, b) (((a) < (b)) ? (a) : (b)) /* mgm_core.cc:28 */
+/* `x + P*w` of update_costW (mgm_core.cc:93-94,99-100,106-107,113-114): whether the reference build rounds it as
+ * one fma or as mul + add depends on what gcc hoisted out of the label loop; bit 2n of the mask = the +-1 term of
+ * neighbour n uses an fma, bit 2n+1 = its P2 term does.  Pinned against the reference binary (tests/test_oracle.py);
+ * with w = 1 or power-of-two penalties every variant gives the same floats. */
+int orc_fma_mask = 0xFA;   /* gcc 13.3 -O3 -march=x86-64-v3 build of mgm_core.cc: n0, n1: mul+add / fma; n2, n3: fma / fma */
+void orc_set_fma_mask(int m) { orc_fma_mask = m; }
+static inline float orc_pw(float x, float P, float w, int use_fma) { return use_fma ? fmaf(P, w, x) : x + P * w; }
+#define ORC_W_V1(n, x, P, w) orc_pw((x), (P), (w), (orc_fma_mask >> (2 * (n))) & 1)
+#define ORC_W_V2(n, x, P, w) orc_pw((x), (P), (w), (orc_fma_mask >> (2 * (n) + 1)) & 1)
 
 /* ------------------------------------------------------------------ census */
 
@@ -183,6 +193,92 @@ void orc_costvolume_census(const float *u, const float *v, int w, int h,
     free(cv); free(cu); free(tmp);
 }
 
+/* The other distances of the reference's table (mgm_costvolume.h:186-197) on one channel, NaN-free images.
+ * Where the reference's -O3 -march=native build contracts a*b+c into one fma (checked against the binary,
+ * tests/test_oracle.py), the fma is written out; this file itself is compiled with -ffp-contract=off. */
+static inline float img_at(const float *a, int w, int x, int y) { return a[(size_t)y * w + x]; }
+
+static float cost_bt(const float *u, const float *v, int w, int x, int y, int qx)
+{   /* BTAD, mgm_costvolume.h:96-124: half-sample interpolants in double ("/2.0"), then float min/max */
+    float IL = img_at(u, w, x, y), ILp = IL, ILm = IL;
+    if (x < w - 1) ILp = (IL + img_at(u, w, x + 1, y)) / 2.0;
+    if (x >= 1) ILm = (IL + img_at(u, w, x - 1, y)) / 2.0;
+    float IR = img_at(v, w, qx, y), IRp = IR, IRm = IR;
+    if (qx < w - 1) IRp = (IR + img_at(v, w, qx + 1, y)) / 2.0;
+    if (qx >= 1) IRm = (IR + img_at(v, w, qx - 1, y)) / 2.0;
+    float IminR = fminf(IRm, fminf(IRp, IR)), ImaxR = fmaxf(IRm, fmaxf(IRp, IR));
+    float IminL = fminf(ILm, fminf(ILp, IL)), ImaxL = fmaxf(ILm, fmaxf(ILp, IL));
+    float dLR = fmaxf(0.f, fmaxf(IL - ImaxR, IminR - IL));
+    float dRL = fmaxf(0.f, fmaxf(IR - ImaxL, IminL - IR));
+    return fabsf(MINF(dLR, dRL));
+}
+
+static float cost_ncc(const float *u, const float *v, int w, int h, int x, int y, int qx, int win)
+{   /* computeC_clippedNCC, mgm_costvolume.h:152-180: window scanned x-major (outer i = x offset) */
+    int hw = win / 2;
+    float mu1 = 0, mu2 = 0, s1 = 0, s2 = 0, prod = 0;
+    int n = 0;
+    for (int i = -hw; i <= hw; i++)
+        for (int j = -hw; j <= hw; j++) {
+            int px = x + i, py = y + j, rx = qx + i;
+            if (px < 0 || px >= w || py < 0 || py >= h || rx < 0 || rx >= w) return ORC_INF;   /* valnan -> NaN */
+            float v1 = img_at(u, w, px, py), v2 = img_at(v, w, rx, py);
+            mu1 += v1; mu2 += v2;
+            s1 = fmaf(v1, v1, s1); s2 = fmaf(v2, v2, s2); prod = fmaf(v1, v2, prod);
+            n++;
+        }
+    mu1 /= n; mu2 /= n; s1 /= n; s2 /= n; prod /= n;
+    float num = fmaf(-mu1, mu2, prod);
+    float den = fmaf(-mu1, mu1, s1) * fmaf(-mu2, mu2, s2);
+    double dd = (0.0000001 > den) ? 0.0000001 : (double)den;
+    float NCC = 0;
+    NCC += num / sqrt(dd);
+    float cl = MINF(NCC, 1.f);
+    cl = (0 > cl) ? 0 : cl;
+    return (1 - cl) * 64;
+}
+
+/* allocate_and_fill_sgm_costvolume (mgm_costvolume.cc:74-174) for any distance, prefilter none (census implies the
+ * census prefilter, :98-102).  cost: 0 census, 1 ad, 2 sd, 3 ncc, 4 btad, 5 btsd. */
+void orc_costvolume(const float *u, const float *v, int w, int h, const int *lo, const int *hi, int gmin, int D,
+                    int win, int zoom, int dct_shift, int cost, float *C)
+{
+    if (cost == 0) { orc_costvolume_census(u, v, w, h, lo, hi, gmin, D, win, zoom, dct_shift, C); return; }
+    size_t npix = (size_t)w * h;
+    float **vs = malloc(sizeof(float *) * zoom);
+    for (int z = 0; z < zoom; z++) {      /* alloc_prefiltered_fourier_subpix_interp :50-60 */
+        vs[z] = malloc(sizeof(float) * npix);
+        orc_shift(v, vs[z], w, h, ((float)z) / ((float)zoom), dct_shift);
+    }
+#pragma omp parallel for
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            size_t p = (size_t)y * w + x;
+            float *Cp = C + p * D;
+            for (int k = 0; k < D; k++) Cp[k] = ORC_INF;
+            int allinvalid = 1;
+            for (int o = lo[p]; o <= hi[p]; o++) {
+                int qx = x + (int)floor((double)o / zoom);
+                const float *vz = vs[goodmod(o, zoom)];
+                float e = ORC_INF;
+                if (qx >= 0 && qx < w) {
+                    float d = img_at(u, w, x, y) - img_at(vz, w, qx, y);
+                    d = (d > -d) ? d : -d;
+                    if (cost == 1) e = d;
+                    else if (cost == 2) e = d * d;
+                    else if (cost == 3) e = cost_ncc(u, vz, w, h, x, y, qx, win);
+                    else { float b = cost_bt(u, vz, w, x, y, qx); e = (cost == 4) ? b : b * b; }
+                }
+                Cp[o - gmin] = e;
+                if (isfinite(e)) allinvalid = 0;
+            }
+            if (allinvalid)
+                for (int o = lo[p]; o <= hi[p]; o++) Cp[o - gmin] = 0;
+        }
+    for (int z = 0; z < zoom; z++) free(vs[z]);
+    free(vs);
+}
+
 /* ------------------------------------------------------------ aggregation */
 
 /* Pass table, mgm_core.cc:884-891: four neighbour offsets, scan orientation. */
@@ -202,7 +298,7 @@ static const orc_pass PASSES[8] = {
  * (dense, INF outside the pixel's range).  Lmin[p] = min of L[p][*]; arg[p] = LAST label
  * attaining it (:1017-1019). */
 static void orc_one_pass(const float *C, const int *lo, const int *hi, int w, int h, int gmin, int D,
-                         float P1, float P2, int tsgm, int pass, float *L, float *Lmin, float *arg)
+                         float P1, float P2, int tsgm, int pass, const float *wgt, float *L, float *Lmin, float *arg)
 {
     const orc_pass *ps = &PASSES[pass];
     int maxii = w, maxjj = h;
@@ -227,6 +323,9 @@ static void orc_one_pass(const float *C, const int *lo, const int *hi, int w, in
             if (!inside) {
                 for (int o = lo[p]; o <= hi[p]; o++) Lp[o - gmin] = Cp[o - gmin];  /* :953 */
             } else {
+                /* -wl / -wr weights: compute_mgm_weights_copyvalue gives every edge of pixel p the value w(p)
+                 * (mgm_weights.h:92-110), read at the CURRENT pixel for each neighbour (mgm_core.cc:981-985) */
+                const float wp = wgt ? wgt[p] : 1.0f;
                 for (int o = lo[p]; o <= hi[p]; o++) {
                     int k0 = o - gmin;
                     float e = 0;
@@ -235,8 +334,8 @@ static void orc_one_pass(const float *C, const int *lo, const int *hi, int w, in
                         float mq = Lmin[q[n]];
                         float a = (k0 - 1 >= 0) ? Lq[k0 - 1] : ORC_INF;
                         float b = (k0 + 1 < D) ? Lq[k0 + 1] : ORC_INF;
-                        float v1 = MINF(a, b) + P1 * 1.0f;
-                        float v2 = mq + P2 * 1.0f;
+                        float v1 = ORC_W_V1(n, MINF(a, b), P1, wp);
+                        float v2 = ORC_W_V2(n, mq, P2, wp);
                         float t = fmin3_(Lq[k0], v1, v2) - mq;
                         if (tsgm == 2) t = t / 2;
                         e += t;
@@ -256,9 +355,19 @@ static void orc_one_pass(const float *C, const int *lo, const int *hi, int w, in
 /* mgm_naive_parallelism (mgm_core.cc:829-1074).  S (dense) receives sum_pass L - (ndir-1) C, passes
  * added in order 0..ndir-1 (the 1-thread order).  disp = first strict minimum over finite S,
  * cost = its value, conf = number of passes whose (last) argmin equals disp. */
+void orc_aggregate_w(const float *C, const int *lo, const int *hi, int w, int h, int gmin, int D,
+                     float P1, float P2, int ndir, int tsgm, int fix_overcount, const float *wgt,
+                     float *S, float *disp, float *cost, float *conf);
 void orc_aggregate(const float *C, const int *lo, const int *hi, int w, int h, int gmin, int D,
                    float P1, float P2, int ndir, int tsgm, int fix_overcount,
                    float *S, float *disp, float *cost, float *conf)
+{
+    orc_aggregate_w(C, lo, hi, w, h, gmin, D, P1, P2, ndir, tsgm, fix_overcount, NULL, S, disp, cost, conf);
+}
+/* wgt: per-pixel regularity weight of this view (-wl / -wr), or NULL = all ones */
+void orc_aggregate_w(const float *C, const int *lo, const int *hi, int w, int h, int gmin, int D,
+                     float P1, float P2, int ndir, int tsgm, int fix_overcount, const float *wgt,
+                     float *S, float *disp, float *cost, float *conf)
 {
     size_t npix = (size_t)w * h, nvox = npix * D;
     float **L = malloc(sizeof(float *) * ndir);
@@ -267,7 +376,7 @@ void orc_aggregate(const float *C, const int *lo, const int *hi, int w, int h, i
 #pragma omp parallel for schedule(dynamic, 1)
     for (int p = 0; p < ndir; p++) {
         float *Lmin = malloc(sizeof(float) * npix);
-        orc_one_pass(C, lo, hi, w, h, gmin, D, P1, P2, tsgm, p, L[p], Lmin, args + (size_t)p * npix);
+        orc_one_pass(C, lo, hi, w, h, gmin, D, P1, P2, tsgm, p, wgt, L[p], Lmin, args + (size_t)p * npix);
         free(Lmin);
     }
 #pragma omp parallel for
@@ -425,7 +534,7 @@ void orc_remove_small_cc(int w, int h, const float *in, float *out, int minarea,
 
 /* One view of mgm_call (mgm_multiscale.cc:161-305): volume, aggregation, refinement, /ZOOM. */
 static void orc_view(const float *u, const float *v, int w, int h, const float *dminI, const float *dmaxI,
-                     const orc_params *P, int zoom, float *disp, float *cost, float *conf)
+                     const orc_params *P, int zoom, const float *wgt, float *disp, float *cost, float *conf)
 {
     int npix = w * h;
     int *lo = malloc(sizeof(int) * npix), *hi = malloc(sizeof(int) * npix);
@@ -434,24 +543,33 @@ static void orc_view(const float *u, const float *v, int w, int h, const float *
     for (int i = 1; i < npix; i++) { if (lo[i] < gmin) gmin = lo[i]; if (hi[i] > gmax) gmax = hi[i]; }
     int D = gmax - gmin + 1;
     float *C = malloc(sizeof(float) * (size_t)npix * D), *S = malloc(sizeof(float) * (size_t)npix * D);
-    orc_costvolume_census(u, v, w, h, lo, hi, gmin, D, P->census_win, zoom, P->dct_shift, C);
+    orc_costvolume(u, v, w, h, lo, hi, gmin, D, P->census_win, zoom, P->dct_shift, P->cost, C);
     float P1 = P->P1 / zoom;                                  /* mgm_multiscale.cc:194-202 */
-    orc_aggregate(C, lo, hi, w, h, gmin, D, P1, P->P2, P->ndir, P->tsgm, P->fix_overcount, S, disp, cost, conf);
+    orc_aggregate_w(C, lo, hi, w, h, gmin, D, P1, P->P2, P->ndir, P->tsgm, P->fix_overcount, wgt, S, disp, cost, conf);
     orc_refine(S, lo, hi, npix, gmin, D, P->refine, disp, cost);
     for (int i = 0; i < npix; i++) disp[i] /= (float)zoom;     /* :253 */
     free(C); free(S); free(lo); free(hi);
 }
 
 /* mgm_call (mgm_multiscale.cc:161-335).  costR: channel 0 of cr (needed by mindiff). */
+void orc_mgm_call_w(const float *u, const float *v, int w, int h,
+                    const float *dminL, const float *dmaxL, const float *dminR, const float *dmaxR,
+                    const orc_params *P, int zoom, const float *wl, const float *wr, float *dl, float *dr, float *confL);
 void orc_mgm_call(const float *u, const float *v, int w, int h,
                   const float *dminL, const float *dmaxL, const float *dminR, const float *dmaxR,
                   const orc_params *P, int zoom, float *dl, float *dr, float *confL)
 {
+    orc_mgm_call_w(u, v, w, h, dminL, dmaxL, dminR, dmaxR, P, zoom, NULL, NULL, dl, dr, confL);
+}
+void orc_mgm_call_w(const float *u, const float *v, int w, int h,
+                    const float *dminL, const float *dmaxL, const float *dminR, const float *dmaxR,
+                    const orc_params *P, int zoom, const float *wl, const float *wr, float *dl, float *dr, float *confL)
+{
     int npix = w * h;
     float *cl = malloc(sizeof(float) * npix), *cr = malloc(sizeof(float) * npix);
     float *confR = malloc(sizeof(float) * npix);
-    orc_view(u, v, w, h, dminL, dmaxL, P, zoom, dl, cl, confL);
-    orc_view(v, u, w, h, dminR, dmaxR, P, zoom, dr, cr, confR);
+    orc_view(u, v, w, h, dminL, dmaxL, P, zoom, wl, dl, cl, confL);
+    orc_view(v, u, w, h, dminR, dmaxR, P, zoom, wr, dr, cr, confR);
     if (P->median) {                                          /* :312-315 */
         float *t = malloc(sizeof(float) * npix);
         orc_median(dl, t, w, h, P->median); memcpy(dl, t, sizeof(float) * npix);
@@ -505,9 +623,18 @@ void orc_remove_small_cc(int w, int h, const float *in, float *out, int minarea,
 /* main() of mgm (main_mgm.cc:80-266) from "images in memory" to "disparity in memory".
  * im1/im2 may hold NaN (no data).  Outputs: disp (left, NaN = invalid), conf
  * (-confidence_consensusL), dispR (right view, -Rd; may be NULL). */
+int orc_mgm_w(const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+              const orc_params *P, const float *wl, const float *wr, float *disp, float *conf, float *dispR);
 int orc_mgm(const float *im1, const float *im2, int w, int h, int dmin, int dmax,
             const orc_params *P, float *disp, float *conf, float *dispR)
 {
+    return orc_mgm_w(im1, im2, w, h, dmin, dmax, P, NULL, NULL, disp, conf, dispR);
+}
+/* wl, wr: the -wl / -wr regularity weight images (both or neither, main_mgm.cc:219-222) */
+int orc_mgm_w(const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+              const orc_params *P, const float *wl, const float *wr, float *disp, float *conf, float *dispR)
+{
+    if (!wl || !wr) wl = wr = NULL;
     int npix = w * h;
     float *u = malloc(sizeof(float) * npix), *v = malloc(sizeof(float) * npix);
     float *a = malloc(sizeof(float) * npix), *b = malloc(sizeof(float) * npix);
@@ -522,7 +649,7 @@ int orc_mgm(const float *im1, const float *im2, int w, int h, int dmin, int dmax
         if (isnan(im2[i])) { c[i] = dmin; d[i] = dmin + 1; }  /* :214-216 (sic: dmin, not -dmax) */
     }
     orc_params Q = *P;                                         /* P1,P2 *= nch with nch = 1 (:194-195) */
-    orc_mgm_call(u, v, w, h, a, b, c, d, &Q, 1, disp, dr, conf);
+    orc_mgm_call_w(u, v, w, h, a, b, c, d, &Q, 1, wl, wr, disp, dr, conf);
     for (int i = 0; i < npix; i++) {                           /* :231-236 */
         if (isnan(im1[i])) disp[i] = NAN;
         if (isnan(im2[i])) dr[i] = NAN;
@@ -634,7 +761,8 @@ void orc_upsample2x_disp(const float *sdisp, int snx, int sny, float *dmin, floa
 
 /* recursive_multiscale, mgm_multiscale.cc:339-410 */
 static void orc_recursive(const float *u, const float *v, int nx, int ny, float *dmin, float *dmax, float *dminR, float *dmaxR,
-                          const orc_params *P, int zoom, int numscales, int scale, float *dl, float *dr, float *confL)
+                          const orc_params *P, int zoom, int numscales, int scale, const float *wl, const float *wr,
+                          float *dl, float *dr, float *confL)
 {
     if (fmax(nx, ny) > 100 && fmin(nx, ny) > 50 && scale < numscales) {
         int sx = (nx + 1) / 2, sy = (ny + 1) / 2, sn = sx * sy;
@@ -647,19 +775,33 @@ static void orc_recursive(const float *u, const float *v, int nx, int ny, float 
         orc_downsample2x_disp(dmax, nx, ny, 1, b);
         orc_downsample2x_disp(dminR, nx, ny, 0, c);
         orc_downsample2x_disp(dmaxR, nx, ny, 1, d);
-        orc_recursive(su, sv, sx, sy, a, b, c, d, P, zoom, numscales, scale + 1, sdl, sdr, sconf);
+        float *swl = NULL, *swr = NULL;                        /* the weight maps follow the pyramid, :375-378 */
+        if (wl && wr) {
+            swl = malloc(sizeof(float) * sn); swr = malloc(sizeof(float) * sn);
+            orc_downsample2x(wl, nx, ny, 0.8f, swl);
+            orc_downsample2x(wr, nx, ny, 0.8f, swr);
+        }
+        orc_recursive(su, sv, sx, sy, a, b, c, d, P, zoom, numscales, scale + 1, swl, swr, sdl, sdr, sconf);
         orc_upsample2x_disp(sdl, sx, sy, dmin, dmax, nx, ny);
         orc_upsample2x_disp(sdr, sx, sy, dminR, dmaxR, nx, ny);
-        free(su); free(sv); free(a); free(b); free(c); free(d); free(sdl); free(sdr); free(sconf);
+        free(su); free(sv); free(a); free(b); free(c); free(d); free(sdl); free(sdr); free(sconf); free(swl); free(swr);
     }
-    orc_mgm_call(u, v, nx, ny, dmin, dmax, dminR, dmaxR, P, zoom, dl, dr, confL);
+    orc_mgm_call_w(u, v, nx, ny, dmin, dmax, dminR, dmaxR, P, zoom, wl, wr, dl, dr, confL);
 }
 
 /* main() of mgm_multi (main_mgm_multi.cc:88-256), memory to memory.  The confidence written by
  * -confidence_consensusL is the one of the full-resolution ZOOM=1 call (the outer `param`, :197-209). */
+int orc_mgm_multi_w(const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+                    const orc_params *P, const float *wl, const float *wr, float *disp, float *conf, float *dispR);
 int orc_mgm_multi(const float *im1, const float *im2, int w, int h, int dmin, int dmax,
                   const orc_params *P, float *disp, float *conf, float *dispR)
 {
+    return orc_mgm_multi_w(im1, im2, w, h, dmin, dmax, P, NULL, NULL, disp, conf, dispR);
+}
+int orc_mgm_multi_w(const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+                    const orc_params *P, const float *wl, const float *wr, float *disp, float *conf, float *dispR)
+{
+    if (!wl || !wr) wl = wr = NULL;
     int npix = w * h;
     float *u = malloc(sizeof(float) * npix), *v = malloc(sizeof(float) * npix);
     float *a = malloc(sizeof(float) * npix), *b = malloc(sizeof(float) * npix);
@@ -672,11 +814,12 @@ int orc_mgm_multi(const float *im1, const float *im2, int w, int h, int dmin, in
         if (isnan(im1[i])) { a[i] = dmin; b[i] = dmin + 1; }
         if (isnan(im2[i])) { c[i] = dmin; d[i] = dmin + 1; }
     }
-    orc_recursive(u, v, w, h, a, b, c, d, P, 1, P->scales, 0, disp, dr, conf);
+    orc_recursive(u, v, w, h, a, b, c, d, P, 1, P->scales, 0, wl, wr, disp, dr, conf);
     if (P->subpix > 1) {                                       /* :203-209 */
         orc_update_dmin_dmax(disp, w, h, a, b, a, b, w, h, 2, 4);
         orc_update_dmin_dmax(dr, w, h, c, d, c, d, w, h, 2, 4);
-        orc_recursive(u, v, w, h, a, b, c, d, P, P->subpix, 0, 0, disp, dr, conf2);
+        /* the half-pixel pass builds a fresh `param` without the weight images (:207): unit weights */
+        orc_recursive(u, v, w, h, a, b, c, d, P, P->subpix, 0, 0, NULL, NULL, disp, dr, conf2);
     }
     if (P->lr_mode == 2) {                                     /* :212-217 */
         float *tl = malloc(sizeof(float) * npix), *tr = malloc(sizeof(float) * npix);

@@ -32,14 +32,18 @@ class OrcParams(ctypes.Structure):
         ("lr_mode", ctypes.c_int), ("lr_tau", ctypes.c_float), ("mindiff", ctypes.c_float),
         ("remove_small_cc", ctypes.c_int), ("subpix", ctypes.c_int), ("scales", ctypes.c_int),
         ("refine", ctypes.c_int), ("fix_overcount", ctypes.c_int), ("dct_shift", ctypes.c_int),
+        ("cost", ctypes.c_int),
     ]
+
+
+COSTS = ("census", "ad", "sd", "ncc", "btad", "btsd")   # -t, index = OrcParams.cost
 
 
 def mgm_params(**kw):
     """Defaults = what s2p sets for algo == 'mgm' (s2p/block_matching.py:155-186)."""
     d = dict(ndir=8, tsgm=3, census_win=5, P1=8.0, P2=32.0, median=1, lr_mode=1, lr_tau=1.0,
              mindiff=-1.0, remove_small_cc=0, subpix=1, scales=-1, refine=1, fix_overcount=1,
-             dct_shift=0)
+             dct_shift=0, cost=0)
     d.update(kw)
     return OrcParams(**d)
 
@@ -48,7 +52,7 @@ def mgm_multi_params(**kw):
     """Defaults = what s2p sets for algo == 'mgm_multi' (s2p/block_matching.py:269-308)."""
     d = dict(ndir=8, tsgm=4, census_win=5, P1=8.0, P2=32.0, median=0, lr_mode=1, lr_tau=1.0,
              mindiff=-1.0, remove_small_cc=25, subpix=2, scales=6, refine=1, fix_overcount=1,
-             dct_shift=0)
+             dct_shift=0, cost=0)
     d.update(kw)
     return OrcParams(**d)
 
@@ -116,29 +120,29 @@ class port:
         return S, disp, cost, conf
 
     @staticmethod
-    def mgm(im1, im2, dmin, dmax, params=None):
-        """-> disp (left), conf, dispR : the `mgm` binary from memory to memory."""
-        params = params or mgm_params()
-        im1, im2 = _f32(im1), _f32(im2)
-        h, w = im1.shape
-        disp = np.empty((h, w), np.float32)
-        conf = np.empty((h, w), np.float32)
-        dispR = np.empty((h, w), np.float32)
-        lib().orc_mgm(_p(im1), _p(im2), w, h, int(dmin), int(dmax), ctypes.byref(params),
-                      _p(disp), _p(conf), _p(dispR))
-        return disp, conf, dispR
+    def mgm(im1, im2, dmin, dmax, params=None, wl=None, wr=None):
+        """-> disp (left), conf, dispR : the `mgm` binary from memory to memory (wl, wr = -wl / -wr weights)."""
+        return port._run("orc_mgm_w", params or mgm_params(), im1, im2, dmin, dmax, wl, wr)
 
     @staticmethod
-    def mgm_multi(im1, im2, dmin, dmax, params=None):
+    def mgm_multi(im1, im2, dmin, dmax, params=None, wl=None, wr=None):
         """-> disp (left), conf, dispR : the `mgm_multi` binary from memory to memory."""
-        params = params or mgm_multi_params()
+        return port._run("orc_mgm_multi_w", params or mgm_multi_params(), im1, im2, dmin, dmax, wl, wr)
+
+    @staticmethod
+    def _run(fn, params, im1, im2, dmin, dmax, wl, wr):
         im1, im2 = _f32(im1), _f32(im2)
         h, w = im1.shape
         disp = np.empty((h, w), np.float32)
         conf = np.empty((h, w), np.float32)
         dispR = np.empty((h, w), np.float32)
-        lib().orc_mgm_multi(_p(im1), _p(im2), w, h, int(dmin), int(dmax), ctypes.byref(params),
-                            _p(disp), _p(conf), _p(dispR))
+        if wl is not None and wr is not None:
+            wl, wr = _f32(wl), _f32(wr)
+            pw = (_p(wl), _p(wr))
+        else:
+            pw = (None, None)
+        getattr(lib(), fn)(_p(im1), _p(im2), w, h, int(dmin), int(dmax), ctypes.byref(params), pw[0], pw[1],
+                           _p(disp), _p(conf), _p(dispR))
         return disp, conf, dispR
 
     @staticmethod
@@ -209,7 +213,7 @@ def _env(params, threads):
 _REFINE = {0: "none", 1: "vfit", 2: "parabola"}
 
 
-def run_ref(im1, im2, dmin, dmax, params, threads=1, extra_env=None, workdir=None, binary=None):
+def run_ref(im1, im2, dmin, dmax, params, threads=1, extra_env=None, workdir=None, binary=None, wl=None, wr=None):
     """Run oracle/_ref/mgm (params.scales < 0) or mgm_multi on in-memory images.
     -> dict(disp, conf, dispR, seconds).  OMP_NUM_THREADS=1 is the parity oracle."""
     import time
@@ -223,9 +227,14 @@ def run_ref(im1, im2, dmin, dmax, params, threads=1, extra_env=None, workdir=Non
     argv = [exe, "-r", str(int(dmin)), "-R", str(int(dmax))]
     if binary == "mgm_multi":
         argv += ["-S", str(params.scales)]
-    argv += ["-s", _REFINE[params.refine], "-t", "census", "-O", str(params.ndir),
-             "-P1", repr(float(params.P1)), "-P2", repr(float(params.P2)),
-             "-confidence_consensusL", c, "-Rd", r, a, b, d]
+    argv += ["-s", _REFINE[params.refine], "-t", COSTS[params.cost], "-O", str(params.ndir),
+             "-P1", repr(float(params.P1)), "-P2", repr(float(params.P2))]
+    if wl is not None and wr is not None:
+        pl, pr = os.path.join(tmp, "wl.pfm"), os.path.join(tmp, "wr.pfm")
+        write_pfm(pl, wl)
+        write_pfm(pr, wr)
+        argv += ["-wl", pl, "-wr", pr]
+    argv += ["-confidence_consensusL", c, "-Rd", r, a, b, d]
     env = _env(params, threads)
     if extra_env:
         env.update(extra_env)
