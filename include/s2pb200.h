@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define S2PB_VERSION 100
+#define S2PB_VERSION 101
 
 enum {
     S2PB_OK = 0,
@@ -66,7 +66,12 @@ typedef struct s2pb_mgm_params {
     int32_t refine;          /* -s           0 none, 1 vfit, 2 parabola                   */
     int32_t fix_overcount;   /* TSGM_FIX_OVERCOUNT                                        */
     int32_t timeout_ms;      /* <= 0: none.  mirrors common.run(timeout=) for mgm*        */
+    int32_t cost;            /* -t           S2PB_COST_*: census (what s2p passes), ad, sd, ncc, btad, btsd */
 } s2pb_mgm_params;
+
+/* -t: the distances of the reference's table (3rdparty/mgm_multi/mgm_costvolume.h:186-197).  census uses the
+ * census prefilter (mgm_costvolume.cc:98-102), the others work on the images; ncc's window is census_win. */
+enum { S2PB_COST_CENSUS = 0, S2PB_COST_AD, S2PB_COST_SD, S2PB_COST_NCC, S2PB_COST_BTAD, S2PB_COST_BTSD, S2PB_COST_COUNT };
 
 typedef struct s2pb_ctx s2pb_ctx;   /* one per (process, GPU); not thread safe */
 
@@ -87,6 +92,15 @@ int          s2pb_default_params(const char *algo, s2pb_mgm_params *p);
 int s2pb_mgm(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h,
              int dmin, int dmax, const s2pb_mgm_params *p,
              float *disp, float *conf, uint8_t *mask, float *disp_right);
+
+/* s2pb_mgm with the regularity weight images of `-wl` / `-wr` (main_mgm.cc:139-140,219-222; what
+ * algo == 'mgm_multi_lsd' passes, s2p/block_matching.py:191-266): wl, wr = w*h float32 each, both or neither.
+ * Every penalty of pixel p is multiplied by w(p) (mgm_weights.h:92-110, mgm_core.cc:981-992); in mgm_multi the
+ * weight maps follow the pyramid (mgm_multiscale.cc:375-378) and the half-pixel pass runs unweighted
+ * (main_mgm_multi.cc:207). */
+int s2pb_mgm_weighted(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h,
+                      int dmin, int dmax, const s2pb_mgm_params *p, const float *wl, const float *wr,
+                      float *disp, float *conf, uint8_t *mask, float *disp_right);
 
 /* Same, device pointers on both sides, enqueued on `stream` (a cudaStream_t
  * passed as void*, NULL = the context's own stream) and NOT synchronised when
@@ -152,10 +166,17 @@ int s2pb_census(s2pb_ctx *ctx, const float *img, int w, int h, int win, uint64_t
  * C: w*h*D float32, slot k <-> label gmin+k, +INF outside the range / image. */
 int s2pb_costvolume(s2pb_ctx *ctx, const float *u, const float *v, int w, int h,
                     const int32_t *lo, const int32_t *hi, int gmin, int D, int win, float *C);
+/* Same for any distance (cost = S2PB_COST_*; win = census or ncc window): mgm_costvolume.h:25-180. */
+int s2pb_costvolume_dist(s2pb_ctx *ctx, const float *u, const float *v, int w, int h,
+                         const int32_t *lo, const int32_t *hi, int gmin, int D, int win, int cost, float *C);
 /* mgm_core.cc:829-1074 on a caller-supplied volume.  S (nullable): w*h*D. */
 int s2pb_aggregate(s2pb_ctx *ctx, const float *C, const int32_t *lo, const int32_t *hi,
                    int w, int h, int gmin, int D, float P1, float P2, int ndir, int tsgm,
                    int fix_overcount, float *S, float *disp, float *cost, float *conf);
+/* Same through the general aggregation flavour: any float costs, optional per-pixel weights (w*h, nullable). */
+int s2pb_aggregate_w(s2pb_ctx *ctx, const float *C, const int32_t *lo, const int32_t *hi,
+                     int w, int h, int gmin, int D, float P1, float P2, int ndir, int tsgm,
+                     int fix_overcount, const float *weights, float *S, float *disp, float *cost, float *conf);
 /* img_tools.h:204-238 */
 int s2pb_median(s2pb_ctx *ctx, const float *in, float *out, int w, int h, int radius);
 /* remove_small_cc.c:9-73 with the intensity threshold 5 of mgm_multiscale.cc:332-333 */

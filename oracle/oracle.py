@@ -94,18 +94,20 @@ class port:
         return out
 
     @staticmethod
-    def costvolume(u, v, lo, hi, gmin, D, win=5, zoom=1, dct_shift=0):
+    def costvolume(u, v, lo, hi, gmin, D, win=5, zoom=1, dct_shift=0, cost=0):
+        """cost: index into COSTS, or its name"""
         u, v = _f32(u), _f32(v)
         h, w = u.shape
         lo = np.ascontiguousarray(lo, np.int32)
         hi = np.ascontiguousarray(hi, np.int32)
         C = np.empty((h, w, D), np.float32)
-        lib().orc_costvolume_census(_p(u), _p(v), w, h, _p(lo, ctypes.c_int), _p(hi, ctypes.c_int),
-                                    gmin, D, win, zoom, dct_shift, _p(C))
+        ci = COSTS.index(cost) if isinstance(cost, str) else int(cost)
+        lib().orc_costvolume(_p(u), _p(v), w, h, _p(lo, ctypes.c_int), _p(hi, ctypes.c_int),
+                             gmin, D, win, zoom, dct_shift, ci, _p(C))
         return C
 
     @staticmethod
-    def aggregate(C, lo, hi, gmin, P1=8.0, P2=32.0, ndir=8, tsgm=3, fix_overcount=1):
+    def aggregate(C, lo, hi, gmin, P1=8.0, P2=32.0, ndir=8, tsgm=3, fix_overcount=1, weights=None):
         C = _f32(C)
         h, w, D = C.shape
         lo = np.ascontiguousarray(lo, np.int32)
@@ -114,9 +116,10 @@ class port:
         disp = np.empty((h, w), np.float32)
         cost = np.empty((h, w), np.float32)
         conf = np.empty((h, w), np.float32)
-        lib().orc_aggregate(_p(C), _p(lo, ctypes.c_int), _p(hi, ctypes.c_int), w, h, gmin, D,
-                            ctypes.c_float(P1), ctypes.c_float(P2), ndir, tsgm, fix_overcount,
-                            _p(S), _p(disp), _p(cost), _p(conf))
+        wgt = _f32(weights) if weights is not None else None
+        lib().orc_aggregate_w(_p(C), _p(lo, ctypes.c_int), _p(hi, ctypes.c_int), w, h, gmin, D,
+                              ctypes.c_float(P1), ctypes.c_float(P2), ndir, tsgm, fix_overcount,
+                              _p(wgt) if wgt is not None else None, _p(S), _p(disp), _p(cost), _p(conf))
         return S, disp, cost, conf
 
     @staticmethod

@@ -22,8 +22,11 @@ class MgmParams(ctypes.Structure):
         ("ndir", c_int32), ("tsgm", c_int32), ("census_win", c_int32), ("P1", c_float), ("P2", c_float),
         ("median", c_int32), ("lr_mode", c_int32), ("lr_tau", c_float), ("mindiff", c_float),
         ("remove_small_cc", c_int32), ("subpix", c_int32), ("scales", c_int32), ("refine", c_int32),
-        ("fix_overcount", c_int32), ("timeout_ms", c_int32),
+        ("fix_overcount", c_int32), ("timeout_ms", c_int32), ("cost", c_int32),
     ]
+
+
+COSTS = ("census", "ad", "sd", "ncc", "btad", "btsd")   # S2PB_COST_* = index; the reference's `-t` names
 
 
 class S2pbError(RuntimeError):
@@ -43,6 +46,8 @@ _SIGNATURES = {
     "s2pb_destroy": (None, [c_void_p]),
     "s2pb_default_params": (c_int, [c_char_p, POINTER(MgmParams)]),
     "s2pb_mgm": (c_int, [c_void_p, _f, _f, c_int, c_int, c_int, c_int, POINTER(MgmParams), _f, _f, POINTER(c_uint8), _f]),
+    "s2pb_mgm_weighted": (c_int, [c_void_p, _f, _f, c_int, c_int, c_int, c_int, POINTER(MgmParams), _f, _f, _f, _f,
+                                  POINTER(c_uint8), _f]),
     "s2pb_mgm_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(MgmParams),
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "s2pb_mgm_batch": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int,
@@ -57,6 +62,10 @@ _SIGNATURES = {
     "s2pb_erode_mask": (c_int, [c_void_p, POINTER(c_uint8), POINTER(c_uint8), c_int, c_int, c_float]),
     "s2pb_census": (c_int, [c_void_p, _f, c_int, c_int, c_int, POINTER(c_uint64)]),
     "s2pb_costvolume": (c_int, [c_void_p, _f, _f, c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int, _f]),
+    "s2pb_costvolume_dist": (c_int, [c_void_p, _f, _f, c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int,
+                                     c_int, _f]),
+    "s2pb_aggregate_w": (c_int, [c_void_p, _f, POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int, c_int, c_float, c_float,
+                                 c_int, c_int, c_int, _f, _f, _f, _f, _f]),
     "s2pb_aggregate": (c_int, [c_void_p, _f, POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int, c_int, c_float, c_float,
                                c_int, c_int, c_int, _f, _f, _f, _f]),
     "s2pb_median": (c_int, [c_void_p, _f, _f, c_int, c_int, c_int]),

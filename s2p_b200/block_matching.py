@@ -1,7 +1,7 @@
 """Drop-in for ``s2p.block_matching`` (boundary #1 of SURVEY.md section 8b).
 
 ``compute_disparity_map`` keeps the reference's signature, file contract and exceptions
-(s2p/block_matching.py:35-336) but, for ``algo in {'mgm', 'mgm_multi'}``, runs the B200 engine
+(s2p/block_matching.py:35-336) but, for ``algo in {'mgm', 'mgm_multi', 'mgm_multi_lsd'}``, runs the B200 engine
 through the C ABI instead of spawning the ``mgm`` / ``mgm_multi`` binaries and the three
 ``plambda`` / ``backflow`` processes of ``create_rejection_mask``.  Any other ``algo`` is handed to
 the original s2p implementation when that package is importable.
@@ -28,7 +28,7 @@ except Exception:
     class MaxDisparityRangeError(Exception):
         pass
 
-_NATIVE = ("mgm", "mgm_multi")
+_NATIVE = ("mgm", "mgm_multi", "mgm_multi_lsd")
 
 
 def disparity_bounds(width, disp_min, disp_max, max_disp_range=None):
@@ -57,16 +57,39 @@ def matcher_params(algo, timeout):
     p.lr_mode = int(cfg["mgm_leftright_control"])
     p.lr_tau = float(cfg["mgm_leftright_threshold"])
     p.mindiff = float(cfg["mgm_mindiff_control"])
-    if algo == "mgm_multi":
+    if algo in ("mgm_multi", "mgm_multi_lsd"):
         mult = float(cfg["stereo_regularity_multiplier"])
-        p.P1, p.P2 = 8.0 * mult, 32.0 * mult
+        base = (12.0, 48.0) if algo == "mgm_multi_lsd" else (8.0, 32.0)     # s2p/block_matching.py:236-237,284-285
+        p.P1, p.P2 = base[0] * mult, base[1] * mult
         p.remove_small_cc = int(cfg["stereo_speckle_filter"])
     p.timeout_ms = int(1000 * timeout) if timeout else 0
     return p
 
 
-def confidence_path(disp):
+def confidence_path(disp, algo="mgm"):
+    if algo == "mgm_multi_lsd":                     # s2p/block_matching.py:238
+        return disp + ".confidence.tif"
     return "{}_confidence.tif".format(os.path.splitext(disp)[0])
+
+
+def lsd_weight_map(im):
+    """Regularity weights of 'mgm_multi_lsd' for one rectified image: the reference's own host pipeline
+    (s2p/block_matching.py:199-218: qauto | lsd | cut | pview segments | plambda "255 x - 255 / 2 pow 0.1 fmax"),
+    run as is -- line-segment detection is host pre-processing, not part of the matcher.  -> float32 (h, w)."""
+    import tempfile
+    width, height = rio.image_size(im)
+    tdir = cfg["temporary_dir"] if os.path.isdir(str(cfg["temporary_dir"])) else None
+    fd, out = tempfile.mkstemp(suffix=".tif", dir=tdir)                               # common.tmpfile, s2p/common.py:50-67
+    os.close(fd)
+    cmd = ("qauto %s | lsd  -  - | cut -d' ' -f1,2,3,4 | pview segments %d %d | "
+           "plambda -  \"255 x - 255 / 2 pow 0.1 fmax\" -o %s" % (im, width, height, out))
+    print("\nRUN: %s" % cmd)
+    try:
+        subprocess.run(cmd, shell=True, check=True)
+        return rio.read_band(out)
+    finally:
+        if os.path.exists(out):
+            os.remove(out)
 
 
 def compute_disparity_map(im1, im2, disp, mask, algo, disp_min=None, disp_max=None, timeout=600,
@@ -97,13 +120,14 @@ def compute_disparity_map(im1, im2, disp, mask, algo, disp_min=None, disp_max=No
     if a.shape != b.shape:
         raise subprocess.CalledProcessError(1, cmd, output="rectified images differ in size")
     try:
-        out = get_engine().mgm(a, b, disp_min, disp_max, matcher_params(algo, timeout), want_mask=True)
+        weights = (lsd_weight_map(im1), lsd_weight_map(im2)) if algo == "mgm_multi_lsd" else None
+        out = get_engine().mgm(a, b, disp_min, disp_max, matcher_params(algo, timeout), want_mask=True, weights=weights)
     except S2pbError as e:
         if e.code == _lib.ERR_TIMEOUT:
             raise subprocess.TimeoutExpired(cmd, timeout) from e
         raise subprocess.CalledProcessError(-e.code, cmd, output=str(e)) from e
     rio.write_float_tiff(disp, out["disp"])
-    rio.write_float_tiff(confidence_path(disp), out["conf"])
+    rio.write_float_tiff(confidence_path(disp, algo), out["conf"])
     rio.write_mask_png(mask, out["mask"])
 
 

@@ -1,4 +1,5 @@
-// agg_inst.cu -- instantiates aggregate_kernel<S2PB_LPL, TSGM> for TSGM = 1..4.
+// agg_inst.cu -- instantiates aggregate_kernel<S2PB_LPL, TSGM, SCALED, GEN> for TSGM = 1..4: census popcounts,
+// census through the scaling table (windows 3 / 7), and the general flavour (float costs / weights).
 #include "agg_dispatch.h"
 #ifndef S2PB_LPL
 #error "compile with -DS2PB_LPL=<labels per lane>"
@@ -7,14 +8,16 @@
 namespace s2pb {
 
 static constexpr int kLPL = S2PB_LPL;
-static constexpr size_t kSmem = AggSmem<kLPL>::bytes;
+static constexpr size_t kSmem = AggSmem<kLPL, false>::bytes, kSmemGen = AggSmem<kLPL, true>::bytes;
 static constexpr int kCtaPerSm = (kLPL <= 4) ? 2 : 1;
 
 template <> int agg_configure_lpl<kLPL>()
 {
     cudaError_t e = cudaSuccess;
-#define CFG(T, S) e = cudaFuncSetAttribute(aggregate_kernel<kLPL, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem); if (e) return -1;
-    CFG(1, false) CFG(2, false) CFG(3, false) CFG(4, false) CFG(1, true) CFG(2, true) CFG(3, true) CFG(4, true)
+#define CFG(T, S, G) e = cudaFuncSetAttribute(aggregate_kernel<kLPL, T, S, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(G ? kSmemGen : kSmem)); if (e) return -1;
+    CFG(1, false, false) CFG(2, false, false) CFG(3, false, false) CFG(4, false, false)
+    CFG(1, true, false) CFG(2, true, false) CFG(3, true, false) CFG(4, true, false)
+    CFG(1, false, true) CFG(2, false, true) CFG(3, false, true) CFG(4, false, true)
 #undef CFG
     return 0;
 }
@@ -27,8 +30,9 @@ template <> int agg_launch_lpl<kLPL>(int tsgm, const AggParams &P, int sm_count,
     if (grid > total) grid = total;
     dim3 block(kAggThreads);
     const bool scaled = P.lut != nullptr;
-#define GO(T) do { if (scaled) aggregate_kernel<kLPL, T, true><<<grid, block, kSmem, st>>>(P); \
-                   else aggregate_kernel<kLPL, T, false><<<grid, block, kSmem, st>>>(P); } while (0)
+#define GO(T) do { if (P.general) aggregate_kernel<kLPL, T, false, true><<<grid, block, kSmemGen, st>>>(P); \
+                   else if (scaled) aggregate_kernel<kLPL, T, true, false><<<grid, block, kSmem, st>>>(P); \
+                   else aggregate_kernel<kLPL, T, false, false><<<grid, block, kSmem, st>>>(P); } while (0)
     switch (tsgm) {
     case 1: GO(1); break;
     case 2: GO(2); break;
@@ -41,4 +45,5 @@ template <> int agg_launch_lpl<kLPL>(int tsgm, const AggParams &P, int sm_count,
 }
 
 }  // namespace s2pb
-static_assert(s2pb::AggSmem<S2PB_LPL>::bytes <= 227 * 1024, "aggregation CTA exceeds the 227 KB of shared memory of an sm_100 SM");
+static_assert(s2pb::AggSmem<S2PB_LPL, false>::bytes <= 227 * 1024 && s2pb::AggSmem<S2PB_LPL, true>::bytes <= 227 * 1024,
+              "aggregation CTA exceeds the 227 KB of shared memory of an sm_100 SM");

@@ -10,6 +10,8 @@
 //   census  u64  [H][W]
 //   C       f16  [H][W][DP]   popcount of the census XOR (exact in f16), +INF = label
 //                             outside the pixel's range or outside the image
+//           f32  [H][W][DP]   instead, for the "general" flavour (GEN): the other distances of the reference's
+//                             table (ad, sd, ncc, btad, btsd) and / or per-pixel regularity weights (-wl / -wr)
 //   L_p     f32  [H][W][DP]   one volume per scan pass p (kept separate so that the
 //                             passes run concurrently and are still summed in the
 //                             reference's 1-thread order 0..7)
@@ -182,7 +184,8 @@ struct PassDesc {
     int strideS, strideI;
     int type;
     int nBands;
-    const __half *C;
+    const void *C;   // __half (census popcounts) or float (GEN) [H][W][DP]
+    const float *W;  // GEN: this view's regularity weight image (-wl / -wr), nullptr = all ones
     float *L;
     float *Lmin;     // minima of the band-closing scanlines only (read back by the next band)
     int *progress;   // [nBands] pixels of the band's last scanline visible in global memory
@@ -194,13 +197,14 @@ struct AggParams {
     int *next_item;
     const int *abort_flag;
     const float *lut;
+    int general;     // 1: GEN flavour (float costs, optional per-pixel weights)
 };
 
 // cp.async pipeline depth in pixel steps (kStage) and slots of the previous-band ring (kR0 > kStage + 1,
 // because pixel 0 is staged ahead of the pipeline); shallower for the widest volumes so the CTA fits 227 KB
-template <int LPL> struct StageCfg {
-    static constexpr int kStage = (LPL <= 12) ? 8 : 2;
-    static constexpr int kR0 = (LPL <= 12) ? 16 : 4;
+template <int LPL, bool GEN = false> struct StageCfg {
+    static constexpr int kStage = GEN ? ((LPL <= 4) ? 8 : (LPL <= 8) ? 4 : 2) : ((LPL <= 12) ? 8 : 2);
+    static constexpr int kR0 = 2 * kStage;
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
@@ -287,15 +291,17 @@ template <int LPL> __device__ __forceinline__ float nb_term(const NbVec<LPL> &n,
 }
 
 // shared memory carve-up of one CTA (floats first, then halfs; every block 16-byte aligned)
-template <int LPL> struct AggSmem {
+template <int LPL, bool GEN = false> struct AggSmem {
     static constexpr int DP = 32 * LPL;
-    static constexpr int kStage = StageCfg<LPL>::kStage, kR0 = StageCfg<LPL>::kR0;
+    static constexpr int kStage = StageCfg<LPL, GEN>::kStage, kR0 = StageCfg<LPL, GEN>::kR0;
+    static constexpr size_t kCostBytes = GEN ? sizeof(float) : sizeof(__half);
     static constexpr size_t ring_off = 0;                                            // float [kNWC][kRing][DP]
     static constexpr size_t ringm_off = ring_off + sizeof(float) * kNWC * kRing * DP; // float [kNWC][kRing]
     static constexpr size_t r0_off = ringm_off + sizeof(float) * kNWC * kRing;        // float [kR0][DP]   previous band
     static constexpr size_t r0m_off = r0_off + sizeof(float) * kR0 * DP;              // float [kR0]
-    static constexpr size_t cst_off = r0m_off + sizeof(float) * kR0;                  // half [kNW][kStage][DP]
-    static constexpr size_t bytes = cst_off + sizeof(__half) * kNW * kStage * DP;
+    static constexpr size_t cst_off = r0m_off + sizeof(float) * kR0;                  // half | float [kNW][kStage][DP]
+    static constexpr size_t wst_off = cst_off + kCostBytes * kNW * kStage * DP;       // float [kNW][kStage]  (GEN: weights)
+    static constexpr size_t bytes = wst_off + (GEN ? sizeof(float) * kNW * kStage : 0);
 };
 
 // smem address (32-bit, shared state space) helpers for cp.async
@@ -317,7 +323,7 @@ template <int NBYTES> __device__ __forceinline__ void warp_cp_async_s(unsigned s
     }
 }
 
-template <int LPL, int TSGM, int TYPE, bool SCALED>
+template <int LPL, int TSGM, int TYPE, bool SCALED, bool GEN>
 __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1, float P2, const float *__restrict__ lut,
                                          const int *abort_flag, unsigned char *smem)
 {
@@ -330,9 +336,11 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     constexpr int SKEW = useE ? 2 : 1;    // scanline s trails scanline s-1 by SKEW pixels
     constexpr int LEAD = useE ? 1 : 0;    // newest previous-scanline pixel needed at position i is i+LEAD
     constexpr int U = useE ? 3 : 2;       // window / history registers rotate with period U: the step loop is unrolled by U
-    using SM = AggSmem<LPL>;
+    using SM = AggSmem<LPL, GEN>;
+    using CT = typename std::conditional<GEN, float, __half>::type;      // stored cost element
     constexpr int kStage = SM::kStage, kR0 = SM::kR0, S = kStage - 1;
-    constexpr int CH = 4 * LPL;           // 16-byte chunks of one pixel's f16 cost vector
+    constexpr int CB = DP * (int)sizeof(CT);   // bytes of one pixel's cost vector
+    constexpr int CH = CB / 16;                // ... in 16-byte chunks
 
     const int nI = pd.nI;
     const int nsteps = (nI + (kNW - 1) * SKEW + U - 1) / U * U;
@@ -355,15 +363,19 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     const float *srcring = (from_r0 ? reinterpret_cast<float *>(smem + SM::r0_off) : ring + (size_t)(k - 1) * kRing * DP) + lane * LPL;
     const float *srcringm = from_r0 ? reinterpret_cast<float *>(smem + SM::r0m_off) : ringm + (k - 1) * kRing;
     const int srcmask = from_r0 ? (kR0 - 1) : (kRing - 1);
-    const __half *cstA = reinterpret_cast<__half *>(smem + SM::cst_off) + (size_t)(2 * k) * kStage * DP + lane * LPL;
-    const __half *cstB = cstA + kStage * DP;
+    const CT *cstA = reinterpret_cast<CT *>(smem + SM::cst_off) + (size_t)(2 * k) * kStage * DP + lane * LPL;
+    const CT *cstB = cstA + kStage * DP;
+    const float *wstA = reinterpret_cast<float *>(smem + SM::wst_off) + (2 * k) * kStage, *wstB = wstA + kStage;   // GEN only
+    const bool weighted = GEN && pd.W != nullptr;
 
     // ---- staging cursors.  Costs: lanes 0-15 copy scanline A, lanes 16-31 scanline B, 16 bytes each.
     const int rsel = lane >> 4, q16 = lane & 15;
     const bool live_st = rsel ? liveB : liveA;
-    const char *csrc = reinterpret_cast<const char *>(pd.C + (rowbaseA + (long long)rsel * pd.strideS) * DP) + 16 * q16;
-    const long long cstep = strideI * (DP * 2);
-    const unsigned cdst = smem_s + (unsigned)SM::cst_off + (unsigned)((2 * k + rsel) * kStage * DP * 2 + 16 * q16);
+    const char *csrc = reinterpret_cast<const char *>(pd.C) + (rowbaseA + (long long)rsel * pd.strideS) * CB + 16 * q16;
+    const long long cstep = strideI * CB;
+    const unsigned cdst = smem_s + (unsigned)SM::cst_off + (unsigned)((2 * k + rsel) * kStage * CB + 16 * q16);
+    const float *wsrc = weighted ? pd.W + rowbaseA + (long long)rsel * pd.strideS : nullptr;
+    const unsigned wdst = smem_s + (unsigned)SM::wst_off + (unsigned)((2 * k + rsel) * kStage * 4);
     int jc = 0;                                               // next pixel of my scanline to stage
     //      previous band's last scanline (warp 0 only)
     const bool stage_prev = prevA && from_r0;
@@ -377,11 +389,15 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
 
     auto stage_cost = [&]() {            // stage pixel jc of my scanline's costs
         if (live_st && jc < nI) {
-            const unsigned d = cdst + (unsigned)((jc & (kStage - 1)) * (DP * 2));
+            const unsigned d = cdst + (unsigned)((jc & (kStage - 1)) * CB);
 #pragma unroll
             for (int q = 0; q < (CH + 15) / 16; q++)
                 if (CH % 16 == 0 || q16 + 16 * q < CH) cp_async16_s(d + 256 * q, csrc + 256 * q);
             csrc += cstep;
+            if (weighted) {
+                if (q16 == 0) cp_async4_s(wdst + (unsigned)((jc & (kStage - 1)) * 4), wsrc);
+                wsrc += strideI;
+            }
         }
         jc++;
     };
@@ -415,59 +431,52 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         dst.m = srcringm[slot];
         fill_edges<LPL>(dst, lane);
     };
-    auto load_cost = [&](const __half *p, float (&c)[LPL]) {
-        HalfPack<LPL> cp = lds_cost<LPL>(p);
+    auto load_cost = [&](const CT *p, float (&c)[LPL]) {
+        if constexpr (GEN) {
+            ld_vec<LPL>(p, c);
+        } else {
+            HalfPack<LPL> cp = lds_cost<LPL>(p);
 #pragma unroll
-        for (int e = 0; e < LPL; e++) {
-            float cc = __half2float(__ushort_as_half(cp.h[e]));
-            if (SCALED) { if (cc >= 0.f && cc < 64.f) cc = lut[(int)cc]; }   // an idle scanline reads unstaged shared memory: never index with it
-            c[e] = cc;
-        }
-    };
-    // L = C + (sum of the neighbours' terms) / TSGM in the reference's order; border pixels keep L = C
-    auto recurse = [&](const float (&c)[LPL], const NbVec<LPL> &nA, const NbVec<LPL> &nB, const NbVec<LPL> &nC,
-                       const NbVec<LPL> &nE, bool border, float (&L)[LPL]) {
-        const float mA = nA.m + P2, mB = nB.m + P2, mC = nC.m + P2, mE = nE.m + P2;
-#pragma unroll
-        for (int e = 0; e < LPL; e++) {
-            float acc;
-            if constexpr (TYPE == 0) {
-                acc = nb_term<LPL>(nA, e, P1, mA);
-                if (TSGM == 2) acc *= 0.5f;
-                if (useCn) { float tt = nb_term<LPL>(nC, e, P1, mC); acc += (TSGM == 2) ? tt * 0.5f : tt; }
-                if (useB)  { float tt = nb_term<LPL>(nB, e, P1, mB); acc += tt; }
-                if (useE)  { float tt = nb_term<LPL>(nE, e, P1, mE); acc += tt; }
-            } else {
-                acc = nb_term<LPL>(nE, e, P1, mE);
-                if (TSGM == 2) acc *= 0.5f;
-                if (useB)  { float tt = nb_term<LPL>(nB, e, P1, mB); acc += (TSGM == 2) ? tt * 0.5f : tt; }
-                if (useCn) { float tt = nb_term<LPL>(nC, e, P1, mC); acc += tt; }
-                if (useA)  { float tt = nb_term<LPL>(nA, e, P1, mA); acc += tt; }
+            for (int e = 0; e < LPL; e++) {
+                float cc = __half2float(__ushort_as_half(cp.h[e]));
+                if (SCALED) { if (cc >= 0.f && cc < 64.f) cc = lut[(int)cc]; }   // an idle scanline reads unstaged shared memory: never index with it
+                c[e] = cc;
             }
-            if constexpr (TSGM == 3) acc = div3_exact(acc);      // acc is finite and >= 0 on interior pixels
-            if constexpr (TSGM == 4) acc = acc * 0.25f;
-            L[e] = border ? c[e] : c[e] + acc;
         }
     };
-    // The same recursion for the warp's two scanlines at once: the float adds / multiplies / fmas of scanline A and
+    // L = C + (sum of the neighbours' terms) / TSGM in the reference's order; border pixels keep L = C.
+    // The recursion runs for the warp's two scanlines at once: the float adds / multiplies / fmas of scanline A and
     // scanline B are issued as packed f32x2 instructions (FADD2 / FMUL2 / FFMA2, sm_100), each lane of a pair
     // rounding exactly like the scalar instruction; the min / min3 stay scalar.  (a*, b*) = neighbours of A, of B.
     auto recurse2 = [&](const float (&cA)[LPL], const float (&cB)[LPL],
                         const NbVec<LPL> &aA, const NbVec<LPL> &aB, const NbVec<LPL> &aC, const NbVec<LPL> &aE,
                         const NbVec<LPL> &bA, const NbVec<LPL> &bB, const NbVec<LPL> &bC, const NbVec<LPL> &bE,
-                        bool borderA, bool borderB, float (&LA)[LPL], float (&LB)[LPL], auto interior_c) {
+                        bool borderA, bool borderB, const float2 wv, float (&LA)[LPL], float (&LB)[LPL], auto interior_c) {
         constexpr bool INTERIOR = decltype(interior_c)::value;     // both pixels are interior: no border select
         const float2 P1v = make_float2(P1, P1), P2v = make_float2(P2, P2);
         const float2 mA = make_float2(aA.m, bA.m), mB = make_float2(aB.m, bB.m), mC = make_float2(aC.m, bC.m), mE = make_float2(aE.m, bE.m);
-        const float2 qA = __fadd2_rn(mA, P2v), qB = __fadd2_rn(mB, P2v), qC = __fadd2_rn(mC, P2v), qE = __fadd2_rn(mE, P2v);
+        // GEN: the penalties are scaled by the current pixel's weight w (update_costW, mgm_core.cc:93-114).  How
+        // `x + P*w` rounds in the reference build (gcc -O3 -march=native: one fma, or the product hoisted out of the
+        // label loop and then added) was pinned against the binary: the P2 term of every neighbour and the P1 term
+        // of the 3rd / 4th neighbour are fmas, the P1 term of the 1st / 2nd is mul + add (oracle/mgm_oracle.c,
+        // orc_fma_mask).  With w = 1 all of these equal the unweighted x + P.
+        const float2 P1w = GEN ? __fmul2_rn(P1v, wv) : P1v;
+        auto qof = [&](const float2 m) { return GEN ? __ffma2_rn(P2v, wv, m) : __fadd2_rn(m, P2v); };
+        const float2 qA = qof(mA), qB = qof(mB), qC = qof(mC), qE = qof(mE);
         const float2 nA = make_float2(-mA.x, -mA.y), nB = make_float2(-mB.x, -mB.y), nC = make_float2(-mC.x, -mC.y), nE = make_float2(-mE.x, -mE.y);
-        auto term = [&](const NbVec<LPL> &na, const NbVec<LPL> &nb, int e, const float2 q, const float2 negm) {
+        // order of the neighbours in the reference's list: type 0 = A, Cn, B, E ; type 1 = E, B, Cn, A
+        constexpr int ordA = (TYPE == 0) ? 0 : 3, ordC = (TYPE == 0) ? 1 : 2, ordB = (TYPE == 0) ? 2 : 1, ordE = (TYPE == 0) ? 3 : 0;
+        auto term = [&](const NbVec<LPL> &na, const NbVec<LPL> &nb, int e, const float2 q, const float2 negm, auto ord_c) {
+            constexpr bool FMA1 = GEN && decltype(ord_c)::value >= 2;
             const float la = (e == 0) ? na.l : na.v[e - 1], ra = (e == LPL - 1) ? na.r : na.v[e + 1];
             const float lb = (e == 0) ? nb.l : nb.v[e - 1], rb = (e == LPL - 1) ? nb.r : nb.v[e + 1];
-            const float2 v1 = __fadd2_rn(make_float2(fminf(la, ra), fminf(lb, rb)), P1v);
+            const float2 mn = make_float2(fminf(la, ra), fminf(lb, rb));
+            const float2 v1 = FMA1 ? __ffma2_rn(P1v, wv, mn) : __fadd2_rn(mn, P1w);
             const float2 t = make_float2(fmin3f(na.v[e], v1.x, q.x), fmin3f(nb.v[e], v1.y, q.y));
             return __fadd2_rn(t, negm);
         };
+        using oA = std::integral_constant<int, ordA>; using oB = std::integral_constant<int, ordB>;
+        using oC = std::integral_constant<int, ordC>; using oE = std::integral_constant<int, ordE>;
         const float2 half2v = make_float2(0.5f, 0.5f), quart = make_float2(0.25f, 0.25f);
         const float r3 = 0.3333333432674407958984375f;
         const float2 r3v = make_float2(r3, r3), m3v = make_float2(-3.0f, -3.0f);
@@ -475,17 +484,17 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         for (int e = 0; e < LPL; e++) {
             float2 acc;
             if constexpr (TYPE == 0) {
-                acc = term(aA, bA, e, qA, nA);
+                acc = term(aA, bA, e, qA, nA, oA{});
                 if (TSGM == 2) acc = __fmul2_rn(acc, half2v);
-                if (useCn) { float2 tt = term(aC, bC, e, qC, nC); if (TSGM == 2) tt = __fmul2_rn(tt, half2v); acc = __fadd2_rn(acc, tt); }
-                if (useB)  acc = __fadd2_rn(acc, term(aB, bB, e, qB, nB));
-                if (useE)  acc = __fadd2_rn(acc, term(aE, bE, e, qE, nE));
+                if (useCn) { float2 tt = term(aC, bC, e, qC, nC, oC{}); if (TSGM == 2) tt = __fmul2_rn(tt, half2v); acc = __fadd2_rn(acc, tt); }
+                if (useB)  acc = __fadd2_rn(acc, term(aB, bB, e, qB, nB, oB{}));
+                if (useE)  acc = __fadd2_rn(acc, term(aE, bE, e, qE, nE, oE{}));
             } else {
-                acc = term(aE, bE, e, qE, nE);
+                acc = term(aE, bE, e, qE, nE, oE{});
                 if (TSGM == 2) acc = __fmul2_rn(acc, half2v);
-                if (useB)  { float2 tt = term(aB, bB, e, qB, nB); if (TSGM == 2) tt = __fmul2_rn(tt, half2v); acc = __fadd2_rn(acc, tt); }
-                if (useCn) acc = __fadd2_rn(acc, term(aC, bC, e, qC, nC));
-                if (useA)  acc = __fadd2_rn(acc, term(aA, bA, e, qA, nA));
+                if (useB)  { float2 tt = term(aB, bB, e, qB, nB, oB{}); if (TSGM == 2) tt = __fmul2_rn(tt, half2v); acc = __fadd2_rn(acc, tt); }
+                if (useCn) acc = __fadd2_rn(acc, term(aC, bC, e, qC, nC, oC{}));
+                if (useA)  acc = __fadd2_rn(acc, term(aA, bA, e, qA, nA, oA{}));
             }
             if constexpr (TSGM == 3) {            // exact x/3, see div3_exact
                 const float2 q0 = __fmul2_rn(acc, r3v);
@@ -545,7 +554,9 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             }
             const bool borderA = (sA == 0) || (iA == 0) || (iA == nI - 1);
             const bool borderB = (iB == 0) || (iB == nI - 1);
-            recurse2(cA, cB, inlineA, xB, xC, xE, wAB, hNew, hC, hE, borderA, borderB, LA, LB, fast_c);
+            float2 wv = make_float2(1.f, 1.f);
+            if (GEN) { if (weighted) { if (actA) wv.x = wstA[iA & (kStage - 1)]; if (actB) wv.y = wstB[iB & (kStage - 1)]; } }
+            recurse2(cA, cB, inlineA, xB, xC, xE, wAB, hNew, hC, hE, borderA, borderB, wv, LA, LB, fast_c);
             const float mAm = vec_min(LA), mBm = vec_min(LB);
             if (actA) {
 #pragma unroll
@@ -597,7 +608,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     cp_async_wait<0>();
 }
 
-template <int LPL, int TSGM, bool SCALED>
+template <int LPL, int TSGM, bool SCALED, bool GEN>
 __global__ void __launch_bounds__(kAggThreads) __maxnreg__((LPL <= 4) ? 112 : 255) aggregate_kernel(const __grid_constant__ AggParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -612,8 +623,8 @@ __global__ void __launch_bounds__(kAggThreads) __maxnreg__((LPL <= 4) ? 112 : 25
         const int band = item / P.nPV, pvi = item - band * P.nPV;
         const PassDesc &pd = P.pv[pvi];
         if (band >= pd.nBands) continue;
-        if (pd.type == 0) run_band<LPL, TSGM, 0, SCALED>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, smem);
-        else run_band<LPL, TSGM, 1, SCALED>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, smem);
+        if (pd.type == 0) run_band<LPL, TSGM, 0, SCALED, GEN>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, smem);
+        else run_band<LPL, TSGM, 1, SCALED, GEN>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, smem);
     }
 }
 

@@ -113,6 +113,130 @@ __global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__r
     }
 }
 
+// ------------------------------------------------------------------ general cost volume (float32)
+
+// The other distances of the reference's table (mgm_costvolume.h:25-57,96-180) on one channel, plus census through
+// the scaling table, written as a float32 slab for the general aggregation flavour.  Arithmetic follows the
+// reference build operation by operation (fmas where gcc contracts them; the NCC quotient in double): the
+// restatement in oracle/mgm_oracle.c is pinned bit for bit against the reference binary for every distance.
+enum { kCostCensus = 0, kCostAD, kCostSD, kCostNCC, kCostBTAD, kCostBTSD };
+struct CostGenParams {
+    const float *u, *v0, *v1;          // this view's image; matched image; matched image shifted by 1/2 px (ZOOMFACTOR 2)
+    const uint64_t *cu, *cv0, *cv1;    // census codes of the same three (cost == census)
+    const float *lut;                  // census: popcount -> cost (mgm_costvolume.h:90-91)
+    const short *lo, *hi;
+    int w, h, gmin, cost, win, zoom;
+    float *C;
+};
+
+__device__ __forceinline__ float bt_cost(const float *__restrict__ u, const float *__restrict__ v, int w, size_t row, int x, int qx)
+{   // BTAD, mgm_costvolume.h:96-124
+    const float IL = u[row + x];
+    float ILp = IL, ILm = IL;
+    if (x < w - 1) ILp = (IL + u[row + x + 1]) * 0.5f;       // "/2.0" in double then back to float: exact halving
+    if (x >= 1) ILm = (IL + u[row + x - 1]) * 0.5f;
+    const float IR = v[row + qx];
+    float IRp = IR, IRm = IR;
+    if (qx < w - 1) IRp = (IR + v[row + qx + 1]) * 0.5f;
+    if (qx >= 1) IRm = (IR + v[row + qx - 1]) * 0.5f;
+    const float IminR = fminf(IRm, fminf(IRp, IR)), ImaxR = fmaxf(IRm, fmaxf(IRp, IR));
+    const float IminL = fminf(ILm, fminf(ILp, IL)), ImaxL = fmaxf(ILm, fmaxf(ILp, IL));
+    const float dLR = fmaxf(0.f, fmaxf(IL - ImaxR, IminR - IL));
+    const float dRL = fmaxf(0.f, fmaxf(IR - ImaxL, IminL - IR));
+    return fabsf(fminf(dLR, dRL));
+}
+__device__ __forceinline__ float ncc_cost(const float *__restrict__ u, const float *__restrict__ v, int w, int h, int x, int y, int qx, int hw)
+{   // computeC_clippedNCC, mgm_costvolume.h:152-180: window scanned x-major; any tap outside either image -> +INF
+    if (x - hw < 0 || x + hw >= w || qx - hw < 0 || qx + hw >= w || y - hw < 0 || y + hw >= h) return S2PB_INF;
+    float mu1 = 0.f, mu2 = 0.f, s1 = 0.f, s2 = 0.f, prod = 0.f;
+    for (int i = -hw; i <= hw; i++)
+        for (int j = -hw; j <= hw; j++) {
+            const size_t r = (size_t)(y + j) * w;
+            const float v1 = u[r + x + i], v2 = v[r + qx + i];
+            mu1 += v1; mu2 += v2;
+            s1 = fmaf(v1, v1, s1); s2 = fmaf(v2, v2, s2); prod = fmaf(v1, v2, prod);
+        }
+    const float n = (float)((2 * hw + 1) * (2 * hw + 1));
+    mu1 = __fdiv_rn(mu1, n); mu2 = __fdiv_rn(mu2, n);
+    s1 = __fdiv_rn(s1, n); s2 = __fdiv_rn(s2, n); prod = __fdiv_rn(prod, n);
+    const float num = fmaf(-mu1, mu2, prod);
+    const float den = fmaf(-mu1, mu1, s1) * fmaf(-mu2, mu2, s2);
+    const double dd = (0.0000001 > (double)den) ? 0.0000001 : (double)den;
+    const float ncc = (float)((double)num / sqrt(dd));
+    float cl = (ncc < 1.f) ? ncc : 1.f;
+    cl = (0.f > cl) ? 0.f : cl;
+    return (1.f - cl) * 64.f;
+}
+
+// one warp per pixel, lanes over labels (slot k <-> label gmin + k), like cost_kernel
+template <int LPL>
+__global__ void cost_gen_kernel(const CostGenParams P)
+{
+    constexpr int DP = 32 * LPL;
+    const int lane = threadIdx.x & 31, w = P.w, hw = P.win / 2;
+    const size_t npix = (size_t)w * P.h;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < npix; p += nwarps) {
+        const int x = (int)(p % w), y = (int)(p / w);
+        const size_t row = p - x;
+        const int l = P.lo[p], hgh = P.hi[p];
+        float c[LPL];
+        bool anyfinite = false;
+#pragma unroll
+        for (int e = 0; e < LPL; e++) {
+            const int o = P.gmin + lane * LPL + e;
+            float val = S2PB_INF;
+            if (o >= l && o <= hgh) {
+                int q = x + o;
+                bool half = false;
+                if (P.zoom == 2) { q = x + (o >> 1); half = (o & 1) != 0; }       // floor(o/2), goodmod(o,2)
+                if (q >= 0 && q < w) {
+                    if (P.cost == kCostCensus) {
+                        const uint64_t *codes = half ? P.cv1 : P.cv0;
+                        val = P.lut[__popcll(P.cu[p] ^ codes[row + q])];
+                    } else {
+                        const float *v = half ? P.v1 : P.v0;
+                        if (P.cost == kCostNCC) val = ncc_cost(P.u, v, w, P.h, x, y, q, hw);
+                        else if (P.cost == kCostBTAD || P.cost == kCostBTSD) {
+                            const float b = bt_cost(P.u, v, w, row, x, q);
+                            val = (P.cost == kCostBTAD) ? b : b * b;
+                        } else {
+                            float d = P.u[p] - v[row + q];
+                            d = (d > -d) ? d : -d;
+                            val = (P.cost == kCostAD) ? d : d * d;
+                        }
+                    }
+                    if (isfinite(val)) anyfinite = true;
+                }
+            }
+            c[e] = val;
+        }
+        if (!__any_sync(0xffffffffu, anyfinite)) {        // mgm_costvolume.cc:166-171
+#pragma unroll
+            for (int e = 0; e < LPL; e++) {
+                const int o = P.gmin + lane * LPL + e;
+                if (o >= l && o <= hgh) c[e] = 0.f;
+            }
+        }
+        st_vec<LPL>(P.C + p * DP + lane * LPL, c);
+    }
+}
+// float slab <-> dense float volume (stage-level API)
+__global__ void pad_cost_kernel(const float *__restrict__ Cin, size_t npix, int D, int DP, float *__restrict__ C)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix * DP) return;
+    size_t p = i / DP; int k = (int)(i % DP);
+    C[i] = k < D ? Cin[p * D + k] : S2PB_INF;
+}
+__global__ void unpad_cost_kernel(const float *__restrict__ C, size_t npix, int D, int DP, float *__restrict__ Cout)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix * D) return;
+    size_t p = i / D; int k = (int)(i % D);
+    Cout[i] = C[p * DP + k];
+}
+
 // float volume (stage-level API) -> f16 slab with +INF padding, and back
 __global__ void pack_cost_kernel(const float *__restrict__ Cin, size_t npix, int D, int DP, __half *__restrict__ C)
 {
@@ -134,7 +258,7 @@ __global__ void unpack_cost_kernel(const __half *__restrict__ C, size_t npix, in
 
 struct WtaParams {
     const float *L[kMaxPasses];
-    const __half *C;
+    const void *C;            // __half slab, or float slab for the general flavour (GEN)
     const short *lo, *hi;     // per-pixel label range (labels, not slots)
     const float *lut;
     int ndir, gmin, fix_overcount, refine;
@@ -172,7 +296,7 @@ __device__ __forceinline__ void parabola3(float v0, float v1, float v2, float &v
 // 128-thread CTAs capped at 56 registers for LPL <= 4: one of them still fits on an SM next to the two resident
 // CTAs of the (issue-bound) aggregation kernel of the NEXT tile, so this memory-bound kernel overlaps it.
 constexpr int kWtaThreads = 128;
-template <int LPL>
+template <int LPL, bool GEN>
 __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 128) wta_kernel(const WtaParams P)
 {
     constexpr int DP = 32 * LPL;
@@ -207,12 +331,16 @@ __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 128
                 }
             }
         }
-        HalfPack<LPL> cp = ld_cost<LPL>(P.C + p * DP + lane * LPL);
+        float cf[LPL];
+        HalfPack<LPL> cp;
+        if constexpr (GEN) ld_vec_cg<LPL>(reinterpret_cast<const float *>(P.C) + p * DP + lane * LPL, cf);
+        else cp = ld_cost<LPL>(reinterpret_cast<const __half *>(P.C) + p * DP + lane * LPL);
         float best = S2PB_INF;
         int bidx = 0x7fffffff;
 #pragma unroll
         for (int e = 0; e < LPL; e++) {
-            float c = cost_value(cp.h[e], P.lut);
+            float c;
+            if constexpr (GEN) c = cf[e]; else c = cost_value(cp.h[e], P.lut);
             if (P.fix_overcount == 1) s[e] = fmaf(-(float)(P.ndir - 1), c, s[e]);
             if (isfinite(s[e]) && best > s[e]) { best = s[e]; bidx = lane * LPL + e; }
         }

@@ -50,7 +50,7 @@ struct ViewWS {
     float *img;            // NaN-free copy
     short *lo, *hi;        // per-pixel label range
     uint64_t *census;
-    __half *C;
+    void *C;               // [H][W][DP] costs: __half (census popcounts) or float (general flavour)
     float *L[kMaxPasses];
     float *Lmin[kMaxPasses];
     int *progress;         // [kMaxPasses][maxBands]
@@ -60,11 +60,13 @@ struct Slot {
     void *base = nullptr;
     size_t bytes = 0;
     int w = 0, h = 0, DP = 0, ndir = 0;
+    int cbytes = 2;               // bytes per stored cost: 2 = f16 census popcounts, 4 = float (general flavour)
     ViewWS v[2];
     int *next_item = nullptr;
     float *lut = nullptr;
     // staging for the host-buffer API
     float *d_in[2] = {nullptr, nullptr};
+    float *d_w[2] = {nullptr, nullptr};           // -wl / -wr weight images of s2pb_mgm_weighted
     float *d_disp = nullptr, *d_conf = nullptr, *d_dispR = nullptr;
     uint8_t *d_mask = nullptr;
     char *io_base = nullptr;
@@ -120,7 +122,7 @@ static int lpl_for(int D)
 }
 static int max_bands(int w, int h) { return ((w > h ? w : h) + kNW - 1) / kNW; }
 
-static int slot_layout(Slot &s, int w, int h, int DP, int ndir, bool allocate)
+static int slot_layout(Slot &s, int w, int h, int DP, int ndir, int cbytes, bool allocate)
 {
     // carve one allocation; called first with allocate=false to size it
     size_t npix = (size_t)w * h, off = 0;
@@ -134,7 +136,7 @@ static int slot_layout(Slot &s, int w, int h, int DP, int ndir, bool allocate)
         o = take(npix * 2); if (allocate) v.lo = (short *)(b + o);
         o = take(npix * 2); if (allocate) v.hi = (short *)(b + o);
         o = take(npix * 8); if (allocate) v.census = (uint64_t *)(b + o);
-        o = take(npix * DP * 2); if (allocate) v.C = (__half *)(b + o);
+        o = take(npix * DP * cbytes); if (allocate) v.C = (void *)(b + o);
         for (int p = 0; p < ndir; p++) {
             o = take(npix * DP * 4); if (allocate) v.L[p] = (float *)(b + o);
             o = take(npix * 4); if (allocate) v.Lmin[p] = (float *)(b + o);
@@ -159,19 +161,20 @@ static int slot_io_ensure(Slot &s, size_t npix)
     if (s.io_pix >= npix) return S2PB_OK;
     if (s.io_base) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.io_base)); s.io_base = nullptr; s.io_pix = 0; }
     size_t stride = align_up(npix * 4, 256);
-    cudaError_t e = cudaMalloc((void **)&s.io_base, stride * 6);
-    if (e != cudaSuccess) { cudaGetLastError(); return fail(S2PB_ERR_NOMEM, "I/O staging of %zu bytes: %s", stride * 6, cudaGetErrorString(e)); }
+    cudaError_t e = cudaMalloc((void **)&s.io_base, stride * 8);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(S2PB_ERR_NOMEM, "I/O staging of %zu bytes: %s", stride * 8, cudaGetErrorString(e)); }
     s.d_in[0] = (float *)s.io_base; s.d_in[1] = (float *)(s.io_base + stride);
     s.d_disp = (float *)(s.io_base + 2 * stride); s.d_conf = (float *)(s.io_base + 3 * stride);
     s.d_dispR = (float *)(s.io_base + 4 * stride); s.d_mask = (uint8_t *)(s.io_base + 5 * stride);
+    s.d_w[0] = (float *)(s.io_base + 6 * stride); s.d_w[1] = (float *)(s.io_base + 7 * stride);
     s.io_pix = npix;
     return S2PB_OK;
 }
 
-static int slot_ensure(s2pb_ctx *ctx, Slot &s, int w, int h, int DP, int ndir)
+static int slot_ensure(s2pb_ctx *ctx, Slot &s, int w, int h, int DP, int ndir, int cbytes = 2)
 {
     Slot probe;
-    slot_layout(probe, w, h, DP, ndir, false);
+    slot_layout(probe, w, h, DP, ndir, cbytes, false);
     if (!s.base || probe.bytes > s.bytes) {
         if (s.base) { CK(cudaStreamSynchronize(s.stream)); CK(cudaFree(s.base)); s.base = nullptr; }
         cudaError_t e = cudaMalloc(&s.base, probe.bytes);
@@ -183,9 +186,9 @@ static int slot_ensure(s2pb_ctx *ctx, Slot &s, int w, int h, int DP, int ndir)
         }
         s.bytes = probe.bytes;
     }
-    s.w = w; s.h = h; s.DP = DP; s.ndir = ndir;
+    s.w = w; s.h = h; s.DP = DP; s.ndir = ndir; s.cbytes = cbytes;
     size_t keep = s.bytes;
-    slot_layout(s, w, h, DP, ndir, true);
+    slot_layout(s, w, h, DP, ndir, cbytes, true);
     s.bytes = keep;
     return S2PB_OK;
 }
@@ -285,6 +288,8 @@ extern "C" int s2pb_default_params(const char *algo, s2pb_mgm_params *p)
         p->tsgm = 3; p->median = 1; p->remove_small_cc = 0; p->subpix = 1; p->scales = -1;
     } else if (!strcmp(algo, "mgm_multi")) {   // s2p/block_matching.py:269-308 ; TSGM default 4 (mgm_multiscale.cc:120)
         p->tsgm = 4; p->median = 0; p->remove_small_cc = 25; p->subpix = 2; p->scales = 6;
+    } else if (!strcmp(algo, "mgm_multi_lsd")) {   // s2p/block_matching.py:191-266 (the caller supplies the LSD weight maps)
+        p->tsgm = 4; p->median = 1; p->remove_small_cc = 25; p->subpix = 2; p->scales = 6; p->P1 = 12.f; p->P2 = 48.f;
     } else return fail(S2PB_ERR_ARG, "unknown algo '%s'", algo);
     return S2PB_OK;
 }
@@ -331,6 +336,7 @@ static int check_params(const s2pb_mgm_params *p, int w, int h, int dmin, int dm
     if (p->scales < 0 && p->lr_mode == 2) return fail(S2PB_ERR_ARG, "TESTLRRL=2 only exists in mgm_multi");
     if (p->scales >= 0 && w > 4000) return fail(S2PB_ERR_UNSUPPORTED, "mgm_multi tiles wider than 4000 px are not supported");
     if (abs(dmin) > 16000 || abs(dmax) > 16000) return fail(S2PB_ERR_ARG, "disparity bounds out of the int16 label range");
+    if (p->cost < 0 || p->cost >= S2PB_COST_COUNT) return fail(S2PB_ERR_ARG, "cost must be one of S2PB_COST_* (got %d)", p->cost);
     return S2PB_OK;
 }
 
@@ -381,8 +387,9 @@ static void fill_pass(PassDesc &pd, int pass, int w, int h)
 }
 
 // Enqueue the 8-pass aggregation of `nviews` views of slot s in ONE persistent launch.
+// general: the float-cost flavour; wgt[vi] = that view's weight image or nullptr (general only)
 static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, int LPL, float P1, float P2, int ndir, int tsgm,
-                            const float *lut, cudaStream_t st)
+                            const float *lut, cudaStream_t st, bool general = false, const float *const *wgt = nullptr)
 {
     AggParams P;
     memset(&P, 0, sizeof P);
@@ -394,11 +401,13 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
             PassDesc &pd = P.pv[P.nPV++];
             fill_pass(pd, p, w, h);
             pd.C = s.v[vi].C; pd.L = s.v[vi].L[p]; pd.Lmin = s.v[vi].Lmin[p];
+            pd.W = (general && wgt) ? wgt[vi] : nullptr;
             pd.progress = s.v[vi].progress + (size_t)p * mb;
             if (pd.nBands > P.maxBands) P.maxBands = pd.nBands;
         }
     }
-    P.P1 = P1; P.P2 = P2; P.next_item = s.next_item; P.abort_flag = ctx->abort_flag; P.lut = lut;
+    P.P1 = P1; P.P2 = P2; P.next_item = s.next_item; P.abort_flag = ctx->abort_flag; P.lut = general ? nullptr : lut;
+    P.general = general ? 1 : 0;
     CK(cudaMemsetAsync(s.next_item, 0, 4, st));
     int r = agg_launch(LPL, tsgm, P, ctx->sm_count, st);
     if (r == -2) return fail(S2PB_ERR_UNSUPPORTED, "no aggregation kernel for %d labels per lane", LPL);
@@ -413,9 +422,14 @@ template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t 
     if (zoom == 2) cost_kernel<LPL, true><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
     else cost_kernel<LPL, false><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
 }
-template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStream_t st)
+template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStream_t st, bool general)
 {
-    wta_kernel<LPL><<<sm * 16, kWtaThreads, 0, st>>>(P);
+    if (general) wta_kernel<LPL, true><<<sm * 16, kWtaThreads, 0, st>>>(P);
+    else wta_kernel<LPL, false><<<sm * 16, kWtaThreads, 0, st>>>(P);
+}
+template <int LPL> static void launch_cost_gen_t(const CostGenParams &P, int sm, cudaStream_t st)
+{
+    cost_gen_kernel<LPL><<<sm * 8, 256, 0, st>>>(P);
 }
 #define LPL_SWITCH(LPL, CALL)                                                             \
     switch (LPL) {                                                                        \
@@ -428,16 +442,23 @@ template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStre
     }
 
 static int launch_cost(s2pb_ctx *ctx, int LPL, const uint64_t *cu, const uint64_t *cv, int w, int h, const short *lo, const short *hi,
-                       int gmin, __half *C, cudaStream_t st, const uint64_t *cv1 = nullptr, int zoom = 1)
+                       int gmin, void *C, cudaStream_t st, const uint64_t *cv1 = nullptr, int zoom = 1)
 {
-    LPL_SWITCH(LPL, launch_cost_t<K>(cu, cv, cv1, zoom, w, h, lo, hi, gmin, C, ctx->sm_count, st));
+    LPL_SWITCH(LPL, launch_cost_t<K>(cu, cv, cv1, zoom, w, h, lo, hi, gmin, (__half *)C, ctx->sm_count, st));
     CK(cudaGetLastError());
     ctx->launches++;
     return S2PB_OK;
 }
-static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t st)
+static int launch_cost_gen(s2pb_ctx *ctx, int LPL, const CostGenParams &P, cudaStream_t st)
 {
-    LPL_SWITCH(LPL, launch_wta_t<K>(P, ctx->sm_count, st));
+    LPL_SWITCH(LPL, launch_cost_gen_t<K>(P, ctx->sm_count, st));
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return S2PB_OK;
+}
+static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t st, bool general = false)
+{
+    LPL_SWITCH(LPL, launch_wta_t<K>(P, ctx->sm_count, st, general));
     CK(cudaGetLastError());
     ctx->launches++;
     return S2PB_OK;
@@ -478,7 +499,10 @@ struct Level {
     float *u, *v;                          // NaN-free images
     float *dminL, *dmaxL, *dminR, *dmaxR;  // per-pixel disparity bounds (pixels, float)
     float *dl, *dr, *conf;                 // results of this level's mgm_call
+    float *wl = nullptr, *wr = nullptr;    // regularity weights of this level (-wl / -wr), or none
 };
+// device weight images at full resolution, both or neither (s2pb_mgm_weighted)
+struct MgmExtra { const float *wl = nullptr, *wr = nullptr; };
 
 static GaussTaps gauss_taps(float sigma)
 {   // mgm_multiscale.cc:66-71
@@ -513,17 +537,23 @@ static int trace_mode() { static int t = -1; if (t < 0) { const char *e = getenv
     fprintf(stderr, "[s2pb] " __VA_ARGS__); fprintf(stderr, " -> %s\n", cudaGetErrorString(e_)); fflush(stderr); } } while (0)
 
 // One mgm_call (mgm_multiscale.cc:161-335) on device images with per-pixel bounds.
-static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb_mgm_params *p, cudaStream_t st)
+static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb_mgm_params *p, cudaStream_t st, bool weighted)
 {
     const int w = L.w, h = L.h, n = w * h;
+    const float *wgt[2] = {weighted ? L.wl : nullptr, weighted ? L.wr : nullptr};
+    const bool general = p->cost != S2PB_COST_CENSUS || (wgt[0] && wgt[1]);
+    const bool census = p->cost == S2PB_COST_CENSUS;
     const size_t npix = (size_t)n;
     dim3 b2(32, 8);
     // ---- integer label ranges of both views and their hulls (one host round trip: the layout depends on them)
     short *lo[2], *hi[2];
     for (int vi = 0; vi < 2; vi++) { lo[vi] = arena_take<short>(s, npix); hi[vi] = arena_take<short>(s, npix); }
     uint64_t *cen_half[2] = {nullptr, nullptr};
-    float *shifted = nullptr;
-    if (zoom == 2) { cen_half[0] = arena_take<uint64_t>(s, npix); cen_half[1] = arena_take<uint64_t>(s, npix); shifted = arena_take<float>(s, npix); }
+    float *shifted = nullptr, *shifted1 = nullptr;
+    if (zoom == 2) {
+        cen_half[0] = arena_take<uint64_t>(s, npix); cen_half[1] = arena_take<uint64_t>(s, npix);
+        shifted = arena_take<float>(s, npix); shifted1 = arena_take<float>(s, npix);
+    }
     float *tl = arena_take<float>(s, npix), *tr = arena_take<float>(s, npix);
     int *lab = arena_take<int>(s, npix), *area = arena_take<int>(s, npix);
     if (!area) return fail(S2PB_ERR_NOMEM, "pyramid arena exhausted");
@@ -546,41 +576,56 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
     }
     int LPL = lpl_for(D);
     if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "a %dx%d level needs %d labels in its dense volume; 512 are supported", w, h, D);
-    int rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir);
+    int rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir, general ? 4 : 2);
     if (rc != S2PB_OK) return rc;
-    TRACE(st, "level %dx%d zoom %d: hull L [%d,%d] R [%d,%d] -> LPL %d", w, h, zoom, gminv[0], gmaxv[0], gminv[1], gmaxv[1], LPL);
+    TRACE(st, "level %dx%d zoom %d: hull L [%d,%d] R [%d,%d] -> LPL %d%s", w, h, zoom, gminv[0], gmaxv[0], gminv[1], gmaxv[1], LPL,
+          general ? " (general flavour)" : "");
     float lut_h[64];
     const float *lut = nullptr;
-    if (cost_lut(p->census_win, lut_h)) { CK(cudaMemcpyAsync(s.lut, lut_h, sizeof lut_h, cudaMemcpyHostToDevice, st)); lut = s.lut; }
+    if (cost_lut(p->census_win, lut_h) || general) { CK(cudaMemcpyAsync(s.lut, lut_h, sizeof lut_h, cudaMemcpyHostToDevice, st)); lut = s.lut; }
     // ---- census (and, for ZOOMFACTOR 2, of the half-pixel shifted matched images)
     const float *img[2] = {L.u, L.v};
-    for (int vi = 0; vi < 2; vi++) {
-        census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(img[vi], w, h, p->census_win / 2, s.v[vi].census);
-        ctx->launches++;
+    float *shf[2] = {shifted, shifted1};       // shf[vi] = shift(img[vi], 1/2) (kept for the image-domain distances)
+    if (census) {
+        for (int vi = 0; vi < 2; vi++) {
+            census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(img[vi], w, h, p->census_win / 2, s.v[vi].census);
+            ctx->launches++;
+        }
     }
     if (zoom == 2) {
         for (int vi = 0; vi < 2; vi++) {      // cen_half[vi] = census(shift(img[vi], 1/2))
-            dct_shift_kernel<<<h, 256, (size_t)7 * w * sizeof(double), st>>>(img[vi], shifted, w, 0.5f);
-            census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(shifted, w, h, p->census_win / 2, cen_half[vi]);
-            ctx->launches += 2;
+            dct_shift_kernel<<<h, 256, (size_t)7 * w * sizeof(double), st>>>(img[vi], shf[vi], w, 0.5f);
+            ctx->launches++;
+            if (census) { census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(shf[vi], w, h, p->census_win / 2, cen_half[vi]); ctx->launches++; }
         }
     }
     CK(cudaGetLastError());
     for (int vi = 0; vi < 2; vi++) {
         s.v[vi].lo = lo[vi]; s.v[vi].hi = hi[vi];
-        rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census, w, h, lo[vi], hi[vi], gminv[vi], s.v[vi].C, st,
-                         zoom == 2 ? cen_half[1 - vi] : nullptr, zoom);
+        if (general) {
+            CostGenParams G;
+            memset(&G, 0, sizeof G);
+            G.u = img[vi]; G.v0 = img[1 - vi]; G.v1 = zoom == 2 ? shf[1 - vi] : nullptr;
+            G.cu = s.v[vi].census; G.cv0 = s.v[1 - vi].census; G.cv1 = zoom == 2 ? cen_half[1 - vi] : nullptr;
+            G.lut = s.lut; G.lo = lo[vi]; G.hi = hi[vi];
+            G.w = w; G.h = h; G.gmin = gminv[vi]; G.cost = p->cost; G.win = p->census_win; G.zoom = zoom;
+            G.C = (float *)s.v[vi].C;
+            rc = launch_cost_gen(ctx, LPL, G, st);
+        } else {
+            rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census, w, h, lo[vi], hi[vi], gminv[vi], s.v[vi].C, st,
+                             zoom == 2 ? cen_half[1 - vi] : nullptr, zoom);
+        }
         if (rc != S2PB_OK) return rc;
     }
     TRACE(st, "  census + cost");
-    rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1 / (float)zoom, p->P2, p->ndir, p->tsgm, lut, st);   // mgm_multiscale.cc:194-202
+    rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1 / (float)zoom, p->P2, p->ndir, p->tsgm, lut, st, general, wgt);   // mgm_multiscale.cc:194-202
     if (rc != S2PB_OK) return rc;
     TRACE(st, "  aggregate");
     for (int vi = 0; vi < 2; vi++) {
         WtaParams W;
         fill_wta(W, s.v[vi], p->ndir, gminv[vi], p, lut, npix);
         W.inv_zoom_div = (float)zoom;
-        rc = launch_wta(ctx, LPL, W, st);
+        rc = launch_wta(ctx, LPL, W, st, general);
         if (rc != S2PB_OK) return rc;
     }
     TRACE(st, "  wta");
@@ -622,10 +667,12 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
 
 // main() of mgm_multi (main_mgm_multi.cc:88-256) + recursive_multiscale (mgm_multiscale.cc:339-410)
 static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *d_im2, int w, int h, int dmin, int dmax,
-                             const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_dispR, cudaStream_t st)
+                             const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_dispR, cudaStream_t st,
+                             const MgmExtra *x)
 {
     const int n = w * h;
     dim3 b2(32, 8);
+    const bool weighted = x && x->wl && x->wr;
     // pyramid shape: downsample while max > 100, min > 50 and scale < -S (mgm_multiscale.cc:362)
     std::vector<Level> lv(1);
     lv[0].w = w; lv[0].h = h;
@@ -636,7 +683,7 @@ static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const f
         lv.push_back(nx);
     }
     size_t need = 0;
-    for (auto &L : lv) need += (size_t)L.w * L.h * 4 * 9 + 9 * 256;
+    for (auto &L : lv) need += (size_t)L.w * L.h * 4 * 11 + 11 * 256;
     need += (size_t)n * (4 * 12 + 2 * 4 + 8 * 2 + 4 * 2) * 2 + (1 << 20);     // scratch of the mgm_calls (two at full size)
     int rc = arena_reset(s, need);
     if (rc != S2PB_OK) return rc;
@@ -647,6 +694,14 @@ static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const f
         L.dminR = arena_take<float>(s, m); L.dmaxR = arena_take<float>(s, m);
         L.dl = arena_take<float>(s, m); L.dr = arena_take<float>(s, m); L.conf = arena_take<float>(s, m);
         if (!L.conf) return fail(S2PB_ERR_NOMEM, "pyramid arena exhausted");
+        if (weighted) {
+            L.wl = arena_take<float>(s, m); L.wr = arena_take<float>(s, m);
+            if (!L.wr) return fail(S2PB_ERR_NOMEM, "pyramid arena exhausted");
+        }
+    }
+    if (weighted) {
+        CK(cudaMemcpyAsync(lv[0].wl, x->wl, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(lv[0].wr, x->wr, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     }
     s.timed = false;
     // level 0: NaN -> 0, initial bounds (main_mgm_multi.cc:160-196; the sentinel for no-data is dmin in both views)
@@ -659,6 +714,11 @@ static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const f
         dim3 g = grid2d(b.w, b.h, b2);
         downsample2x_kernel<<<g, b2, 0, st>>>(a.u, a.w, a.h, T, b.u, b.w, b.h);
         downsample2x_kernel<<<g, b2, 0, st>>>(a.v, a.w, a.h, T, b.v, b.w, b.h);
+        if (weighted) {                        // the weight maps follow the pyramid, mgm_multiscale.cc:375-378
+            downsample2x_kernel<<<g, b2, 0, st>>>(a.wl, a.w, a.h, T, b.wl, b.w, b.h);
+            downsample2x_kernel<<<g, b2, 0, st>>>(a.wr, a.w, a.h, T, b.wr, b.w, b.h);
+            ctx->launches += 2;
+        }
         downsample2x_disp_kernel<<<g, b2, 0, st>>>(a.dminL, a.w, a.h, 0, b.dminL, b.w, b.h);
         downsample2x_disp_kernel<<<g, b2, 0, st>>>(a.dmaxL, a.w, a.h, 1, b.dmaxL, b.w, b.h);
         downsample2x_disp_kernel<<<g, b2, 0, st>>>(a.dminR, a.w, a.h, 0, b.dminR, b.w, b.h);
@@ -686,7 +746,7 @@ static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const f
             CK(cudaGetLastError());
         }
         s.arena_off = arena_mark;
-        rc = mgm_call_level(ctx, s, L, 1, p, st);
+        rc = mgm_call_level(ctx, s, L, 1, p, st, weighted);
         if (rc != S2PB_OK) return rc;
     }
     Level &L0 = lv[0];
@@ -700,7 +760,7 @@ static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const f
         ctx->launches += 2;
         L0.dminL = a; L0.dmaxL = b; L0.dminR = c; L0.dmaxR = d;
         s.arena_off = mark2;
-        rc = mgm_call_level(ctx, s, L0, p->subpix, p, st);
+        rc = mgm_call_level(ctx, s, L0, p->subpix, p, st, false);   // fresh `param` without the weight images (main_mgm_multi.cc:207)
         if (rc != S2PB_OK) return rc;
     }
     float *outL = d_disp;
@@ -727,9 +787,12 @@ static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const f
 
 static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *d_im2, int w, int h, int dmin, int dmax,
                        const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_dispR, cudaStream_t st,
-                       int nodata_hint)
+                       int nodata_hint, const MgmExtra *x = nullptr)
 {
-    if (p->scales >= 0) return mgm_multi_enqueue(ctx, s, d_im1, d_im2, w, h, dmin, dmax, p, d_disp, d_conf, d_mask, d_dispR, st);
+    if (p->scales >= 0) return mgm_multi_enqueue(ctx, s, d_im1, d_im2, w, h, dmin, dmax, p, d_disp, d_conf, d_mask, d_dispR, st, x);
+    const float *wgt[2] = {x ? x->wl : nullptr, x ? x->wr : nullptr};
+    const bool census = p->cost == S2PB_COST_CENSUS;
+    const bool general = !census || (wgt[0] && wgt[1]);
     const size_t npix = (size_t)w * h;
     const int n = (int)npix;
     if (nodata_hint < 0) {     // unknown: look (costs one stream synchronisation)
@@ -742,12 +805,12 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
     int gminv[2], gmaxv[2];
     int LPL = plan_labels(dmin, dmax, (nodata_hint & 2) != 0, gminv, gmaxv);
     if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "disparity range [%d,%d] needs more than the 512 labels supported", dmin, dmax);
-    int rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir);
+    int rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir, general ? 4 : 2);
     if (rc != S2PB_OK) return rc;
 
     float lut_h[64];
     const float *lut = nullptr;
-    if (cost_lut(p->census_win, lut_h)) {
+    if (cost_lut(p->census_win, lut_h) || general) {
         CK(cudaMemcpyAsync(s.lut, lut_h, sizeof lut_h, cudaMemcpyHostToDevice, st));
         lut = s.lut;
     }
@@ -759,26 +822,37 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
     for (int vi = 0; vi < 2; vi++) {
         int lo_all = vi == 0 ? dmin : -dmax, hi_all = vi == 0 ? dmax : -dmin;
         prepare_view_kernel<<<(n + 255) / 256, 256, 0, st>>>(im[vi], n, lo_all, hi_all, dmin, s.v[vi].img, s.v[vi].lo, s.v[vi].hi);
-        census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].img, w, h, p->census_win / 2, s.v[vi].census);
-        ctx->launches += 2;
+        ctx->launches++;
+        if (census) { census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].img, w, h, p->census_win / 2, s.v[vi].census); ctx->launches++; }
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(s.ev[1], st));
     // ---- cost volumes: view 0 = left reference, view 1 = right reference (mgm_multiscale.cc:222,270)
     for (int vi = 0; vi < 2; vi++) {
-        rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census, w, h, s.v[vi].lo, s.v[vi].hi, gminv[vi], s.v[vi].C, st);
+        if (general) {
+            CostGenParams G;
+            memset(&G, 0, sizeof G);
+            G.u = s.v[vi].img; G.v0 = s.v[1 - vi].img;
+            G.cu = s.v[vi].census; G.cv0 = s.v[1 - vi].census;
+            G.lut = s.lut; G.lo = s.v[vi].lo; G.hi = s.v[vi].hi;
+            G.w = w; G.h = h; G.gmin = gminv[vi]; G.cost = p->cost; G.win = p->census_win; G.zoom = 1;
+            G.C = (float *)s.v[vi].C;
+            rc = launch_cost_gen(ctx, LPL, G, st);
+        } else {
+            rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census, w, h, s.v[vi].lo, s.v[vi].hi, gminv[vi], s.v[vi].C, st);
+        }
         if (rc != S2PB_OK) return rc;
     }
     CK(cudaEventRecord(s.ev[2], st));
     // ---- 8-pass MGM of both views in one persistent launch
-    rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1, p->P2, p->ndir, p->tsgm, lut, st);
+    rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt);
     if (rc != S2PB_OK) return rc;
     CK(cudaEventRecord(s.ev[3], st));
     // ---- WTA + consensus + sub-pixel
     for (int vi = 0; vi < 2; vi++) {
         WtaParams W;
         fill_wta(W, s.v[vi], p->ndir, gminv[vi], p, lut, npix);
-        rc = launch_wta(ctx, LPL, W, st);
+        rc = launch_wta(ctx, LPL, W, st, general);
         if (rc != S2PB_OK) return rc;
     }
     CK(cudaEventRecord(s.ev[4], st));
@@ -869,7 +943,8 @@ static bool is_pinned_host(const void *p)
 // stage the inputs of one tile through pinned memory and enqueue everything on the slot's stream
 static int mgm_host_enqueue(s2pb_ctx *ctx, Slot &s, const float *im1, const float *im2, int w, int h, int dmin, int dmax,
                             const s2pb_mgm_params *p, bool want_mask, bool want_right,
-                            float *o_disp = nullptr, float *o_conf = nullptr, uint8_t *o_mask = nullptr)
+                            float *o_disp = nullptr, float *o_conf = nullptr, uint8_t *o_mask = nullptr,
+                            const float *wl = nullptr, const float *wr = nullptr)
 {
     size_t npix = (size_t)w * h;
     int rc = slot_host_ensure(s, npix);
@@ -891,8 +966,14 @@ static int mgm_host_enqueue(s2pb_ctx *ctx, Slot &s, const float *im1, const floa
     if (rc != S2PB_OK) return rc;
     CK(cudaMemcpyAsync(s.d_in[0], src1, npix * 4, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.d_in[1], src2, npix * 4, cudaMemcpyHostToDevice, s.stream));
+    MgmExtra x;
+    if (wl && wr) {        // not a hot path: plain (driver-staged) copies of the caller's weight images
+        CK(cudaMemcpyAsync(s.d_w[0], wl, npix * 4, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_w[1], wr, npix * 4, cudaMemcpyHostToDevice, s.stream));
+        x.wl = s.d_w[0]; x.wr = s.d_w[1];
+    }
     rc = mgm_enqueue(ctx, s, s.d_in[0], s.d_in[1], w, h, dmin, dmax, p, s.d_disp, s.d_conf, want_mask ? s.d_mask : nullptr,
-                     want_right ? s.d_dispR : nullptr, s.stream, sec_nodata ? 2 : 0);
+                     want_right ? s.d_dispR : nullptr, s.stream, sec_nodata ? 2 : 0, &x);
     if (rc != S2PB_OK) return rc;
     // results go straight into the caller's buffers when those are page-locked (o_* != nullptr), else to the staging block
     s.direct_out = o_disp && o_conf && is_pinned_host(o_disp) && is_pinned_host(o_conf) && (!want_mask || (o_mask && is_pinned_host(o_mask)));
@@ -907,12 +988,20 @@ static int mgm_host_enqueue(s2pb_ctx *ctx, Slot &s, const float *im1, const floa
 extern "C" int s2pb_mgm(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h, int dmin, int dmax,
                         const s2pb_mgm_params *p, float *disp, float *conf, uint8_t *mask, float *disp_right)
 {
+    return s2pb_mgm_weighted(ctx, im1, im2, w, h, dmin, dmax, p, nullptr, nullptr, disp, conf, mask, disp_right);
+}
+
+extern "C" int s2pb_mgm_weighted(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+                                 const s2pb_mgm_params *p, const float *wl, const float *wr,
+                                 float *disp, float *conf, uint8_t *mask, float *disp_right)
+{
     if (!ctx || !im1 || !im2 || !disp || !conf) return fail(S2PB_ERR_ARG, "null argument");
+    if ((wl == nullptr) != (wr == nullptr)) return fail(S2PB_ERR_ARG, "the weight images come in pairs (-wl and -wr)");
     int rc = check_params(p, w, h, dmin, dmax);
     if (rc != S2PB_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[0];
-    rc = mgm_host_enqueue(ctx, s, im1, im2, w, h, dmin, dmax, p, mask != nullptr, disp_right != nullptr, disp, conf, mask);
+    rc = mgm_host_enqueue(ctx, s, im1, im2, w, h, dmin, dmax, p, mask != nullptr, disp_right != nullptr, disp, conf, mask, wl, wr);
     if (rc != S2PB_OK) return rc;
     rc = wait_with_timeout(ctx, s.stream, p->timeout_ms);
     if (rc != S2PB_OK) return rc;
@@ -1083,6 +1172,96 @@ extern "C" int s2pb_costvolume(s2pb_ctx *ctx, const float *u, const float *v, in
     return S2PB_OK;
 }
 
+extern "C" int s2pb_costvolume_dist(s2pb_ctx *ctx, const float *u, const float *v, int w, int h, const int32_t *lo, const int32_t *hi,
+                                    int gmin, int D, int win, int cost, float *C)
+{
+    if (!ctx || !u || !v || !lo || !hi || !C || w < 1 || h < 1 || D < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    if (win != 3 && win != 5 && win != 7) return fail(S2PB_ERR_ARG, "window must be 3, 5 or 7");
+    if (cost < 0 || cost >= S2PB_COST_COUNT) return fail(S2PB_ERR_ARG, "cost must be one of S2PB_COST_*");
+    CK(cudaSetDevice(ctx->device));
+    int LPL = lpl_for(D);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "too many labels");
+    const int DP = 32 * LPL;
+    size_t npix = (size_t)w * h, tot = npix * D;
+    cudaStream_t st = ctx->slots[0].stream;
+    DevBuf du, dv, cu, cv, dlo, dhi, dC, dCf, dlut;
+    ALLOC(du, npix * 4); ALLOC(dv, npix * 4); ALLOC(cu, npix * 8); ALLOC(cv, npix * 8);
+    ALLOC(dC, npix * DP * 4); ALLOC(dCf, tot * 4); ALLOC(dlut, 256);
+    int rc = upload_ranges(lo, hi, npix, gmin, D, dlo, dhi, st);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaMemcpyAsync(du.p, u, npix * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dv.p, v, npix * 4, cudaMemcpyHostToDevice, st));
+    float lut_h[64];
+    cost_lut(win, lut_h);
+    CK(cudaMemcpyAsync(dlut.p, lut_h, 256, cudaMemcpyHostToDevice, st));
+    if (cost == S2PB_COST_CENSUS) {
+        dim3 b2(32, 8);
+        census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(du.as<float>(), w, h, win / 2, cu.as<uint64_t>());
+        census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dv.as<float>(), w, h, win / 2, cv.as<uint64_t>());
+        ctx->launches += 2;
+    }
+    CostGenParams G;
+    memset(&G, 0, sizeof G);
+    G.u = du.as<float>(); G.v0 = dv.as<float>(); G.cu = cu.as<uint64_t>(); G.cv0 = cv.as<uint64_t>();
+    G.lut = dlut.as<float>(); G.lo = dlo.as<short>(); G.hi = dhi.as<short>();
+    G.w = w; G.h = h; G.gmin = gmin; G.cost = cost; G.win = win; G.zoom = 1; G.C = dC.as<float>();
+    rc = launch_cost_gen(ctx, LPL, G, st);
+    if (rc != S2PB_OK) return rc;
+    unpad_cost_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dC.as<float>(), npix, D, DP, dCf.as<float>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(C, dCf.p, tot * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
+extern "C" int s2pb_aggregate_w(s2pb_ctx *ctx, const float *C, const int32_t *lo, const int32_t *hi, int w, int h, int gmin, int D,
+                                float P1, float P2, int ndir, int tsgm, int fix_overcount, const float *weights,
+                                float *S, float *disp, float *cost, float *conf)
+{
+    if (!ctx || !C || !lo || !hi || !disp || w < 2 || h < 2 || D < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    if (ndir != 2 && ndir != 4 && ndir != 8) return fail(S2PB_ERR_ARG, "ndir must be 2, 4 or 8");
+    if (tsgm < 1 || tsgm > 4) return fail(S2PB_ERR_ARG, "tsgm must be 1..4");
+    CK(cudaSetDevice(ctx->device));
+    int LPL = lpl_for(D);
+    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "too many labels");
+    const int DP = 32 * LPL;
+    size_t npix = (size_t)w * h, tot = npix * D;
+    Slot &s = ctx->slots[0];
+    cudaStream_t st = s.stream;
+    int rc = slot_ensure(ctx, s, w, h, DP, ndir, 4);
+    if (rc != S2PB_OK) return rc;
+    DevBuf dCf, dlo, dhi, dS, dW;
+    ALLOC(dCf, tot * 4);
+    if (S) ALLOC(dS, tot * 4);
+    if (weights) { ALLOC(dW, npix * 4); CK(cudaMemcpyAsync(dW.p, weights, npix * 4, cudaMemcpyHostToDevice, st)); }
+    rc = upload_ranges(lo, hi, npix, gmin, D, dlo, dhi, st);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaMemcpyAsync(dCf.p, C, tot * 4, cudaMemcpyHostToDevice, st));
+    size_t totp = npix * DP;
+    pad_cost_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(dCf.as<float>(), npix, D, DP, (float *)s.v[0].C);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    const float *wgt[2] = {weights ? dW.as<float>() : nullptr, nullptr};
+    rc = launch_aggregate(ctx, s, 1, w, h, LPL, P1, P2, ndir, tsgm, nullptr, st, true, wgt);
+    if (rc != S2PB_OK) return rc;
+    s2pb_mgm_params prm;
+    s2pb_default_params("mgm", &prm);
+    prm.fix_overcount = fix_overcount; prm.refine = 0;
+    WtaParams W;
+    fill_wta(W, s.v[0], ndir, gmin, &prm, nullptr, npix);
+    W.lo = dlo.as<short>(); W.hi = dhi.as<short>();
+    W.S = S ? dS.as<float>() : nullptr; W.Dout = D;
+    rc = launch_wta(ctx, LPL, W, st, true);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaMemcpyAsync(disp, s.v[0].disp, npix * 4, cudaMemcpyDeviceToHost, st));
+    if (cost) CK(cudaMemcpyAsync(cost, s.v[0].cost, npix * 4, cudaMemcpyDeviceToHost, st));
+    if (conf) CK(cudaMemcpyAsync(conf, s.v[0].conf, npix * 4, cudaMemcpyDeviceToHost, st));
+    if (S) CK(cudaMemcpyAsync(S, dS.p, tot * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return S2PB_OK;
+}
+
 extern "C" int s2pb_aggregate(s2pb_ctx *ctx, const float *C, const int32_t *lo, const int32_t *hi, int w, int h, int gmin, int D,
                               float P1, float P2, int ndir, int tsgm, int fix_overcount, float *S, float *disp, float *cost, float *conf)
 {
@@ -1110,7 +1289,7 @@ extern "C" int s2pb_aggregate(s2pb_ctx *ctx, const float *C, const int32_t *lo, 
     if (rc != S2PB_OK) return rc;
     CK(cudaMemcpyAsync(dCf.p, C, tot * 4, cudaMemcpyHostToDevice, st));
     size_t totp = npix * DP;
-    pack_cost_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(dCf.as<float>(), npix, D, DP, s.v[0].C);
+    pack_cost_kernel<<<(unsigned)((totp + 255) / 256), 256, 0, st>>>(dCf.as<float>(), npix, D, DP, (__half *)s.v[0].C);
     ctx->launches++;
     CK(cudaGetLastError());
     rc = launch_aggregate(ctx, s, 1, w, h, LPL, P1, P2, ndir, tsgm, nullptr, st);

@@ -16,11 +16,17 @@ from ._lib import MgmParams, S2pbError  # noqa: F401  (re-exported)
 
 
 def default_params(algo="mgm", **overrides):
+    """What s2p sets for ``algo`` ('mgm', 'mgm_multi', 'mgm_multi_lsd'), then the overrides; ``cost`` may be the
+    reference's ``-t`` name ('census', 'ad', 'sd', 'ncc', 'btad', 'btsd') or its S2PB_COST_* index."""
     p = MgmParams()
     _lib.check(_lib.lib().s2pb_default_params(algo.encode(), ctypes.byref(p)))
     for k, v in overrides.items():
         if not hasattr(p, k):
             raise TypeError("unknown matcher parameter %r" % k)
+        if k == "cost" and isinstance(v, str):
+            if v not in _lib.COSTS:
+                raise ValueError("unknown distance %r (one of %s)" % (v, ", ".join(_lib.COSTS)))
+            v = _lib.COSTS.index(v)
         setattr(p, k, v)
     return p
 
@@ -64,19 +70,26 @@ class Engine:
         self.close()
 
     # ------------------------------------------------------------------ matcher
-    def mgm(self, im1, im2, dmin, dmax, params=None, want_mask=True, want_right=False):
-        """-> dict(disp, conf, mask[, disp_right]) for one rectified pair (host arrays)."""
+    def mgm(self, im1, im2, dmin, dmax, params=None, want_mask=True, want_right=False, weights=None):
+        """-> dict(disp, conf, mask[, disp_right]) for one rectified pair (host arrays).
+        ``weights`` = (wl, wr): the regularity weight images of ``-wl`` / ``-wr`` (mgm_multi_lsd)."""
         p = params or default_params("mgm")
         im1, im2 = _f32(im1), _f32(im2)
         if im1.shape != im2.shape or im1.ndim != 2:
             raise ValueError("im1 and im2 must be 2-D arrays of the same shape")
         h, w = im1.shape
+        wl = wr = None
+        if weights is not None:
+            wl, wr = _f32(weights[0]), _f32(weights[1])
+            if wl.shape != im1.shape or wr.shape != im1.shape:
+                raise ValueError("the weight images must have the shape of the rectified images")
         disp = np.empty((h, w), np.float32)
         conf = np.empty((h, w), np.float32)
         mask = np.empty((h, w), np.uint8) if want_mask else None
         right = np.empty((h, w), np.float32) if want_right else None
-        _lib.check(self._L.s2pb_mgm(
-            self._ctx, _fp(im1), _fp(im2), w, h, int(dmin), int(dmax), ctypes.byref(p), _fp(disp), _fp(conf),
+        _lib.check(self._L.s2pb_mgm_weighted(
+            self._ctx, _fp(im1), _fp(im2), w, h, int(dmin), int(dmax), ctypes.byref(p),
+            _fp(wl) if wl is not None else None, _fp(wr) if wr is not None else None, _fp(disp), _fp(conf),
             mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if want_mask else None,
             _fp(right) if want_right else None))
         out = dict(disp=disp, conf=conf, mask=mask)
@@ -179,17 +192,24 @@ class Engine:
         _lib.check(self._L.s2pb_census(self._ctx, _fp(img), w, h, win, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
         return out
 
-    def costvolume(self, u, v, lo, hi, gmin, D, win=5):
+    def costvolume(self, u, v, lo, hi, gmin, D, win=5, cost=None):
+        """cost=None: the census / f16 path of the hot matcher; otherwise one of _lib.COSTS through the general path."""
         u, v = _f32(u), _f32(v)
         h, w = u.shape
         lo = np.ascontiguousarray(lo, np.int32)
         hi = np.ascontiguousarray(hi, np.int32)
         C = np.empty((h, w, D), np.float32)
         ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
-        _lib.check(self._L.s2pb_costvolume(self._ctx, _fp(u), _fp(v), w, h, ip(lo), ip(hi), int(gmin), int(D), win, _fp(C)))
+        if cost is None:
+            _lib.check(self._L.s2pb_costvolume(self._ctx, _fp(u), _fp(v), w, h, ip(lo), ip(hi), int(gmin), int(D), win, _fp(C)))
+        else:
+            ci = _lib.COSTS.index(cost) if isinstance(cost, str) else int(cost)
+            _lib.check(self._L.s2pb_costvolume_dist(self._ctx, _fp(u), _fp(v), w, h, ip(lo), ip(hi), int(gmin), int(D), win, ci, _fp(C)))
         return C
 
-    def aggregate(self, C, lo, hi, gmin, P1=8.0, P2=32.0, ndir=8, tsgm=3, fix_overcount=1, want_S=True):
+    def aggregate(self, C, lo, hi, gmin, P1=8.0, P2=32.0, ndir=8, tsgm=3, fix_overcount=1, want_S=True, weights=None,
+                  general=False):
+        """general / weights: the float-cost aggregation flavour (any costs, optional per-pixel weight image)."""
         C = _f32(C)
         h, w, D = C.shape
         lo = np.ascontiguousarray(lo, np.int32)
@@ -199,8 +219,14 @@ class Engine:
         cost = np.empty((h, w), np.float32)
         conf = np.empty((h, w), np.float32)
         ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
-        _lib.check(self._L.s2pb_aggregate(self._ctx, _fp(C), ip(lo), ip(hi), w, h, int(gmin), D, P1, P2, ndir, tsgm,
-                                          fix_overcount, _fp(S) if want_S else None, _fp(disp), _fp(cost), _fp(conf)))
+        if general or weights is not None:
+            wgt = _f32(weights) if weights is not None else None
+            _lib.check(self._L.s2pb_aggregate_w(self._ctx, _fp(C), ip(lo), ip(hi), w, h, int(gmin), D, P1, P2, ndir, tsgm,
+                                                fix_overcount, _fp(wgt) if wgt is not None else None,
+                                                _fp(S) if want_S else None, _fp(disp), _fp(cost), _fp(conf)))
+        else:
+            _lib.check(self._L.s2pb_aggregate(self._ctx, _fp(C), ip(lo), ip(hi), w, h, int(gmin), D, P1, P2, ndir, tsgm,
+                                              fix_overcount, _fp(S) if want_S else None, _fp(disp), _fp(cost), _fp(conf)))
         return S, disp, cost, conf
 
     def median(self, img, radius=1):

@@ -141,8 +141,7 @@ def test_against_reference_golden_vectors(engine, name):
     from s2p_b200.engine import default_params
     ref, sec, dmin, dmax, kw = G.inputs(name)
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
-    kw = dict(kw)
-    algo = kw.pop("_algo", "mgm")
+    algo, kw = G.split_kw(kw)
     out = engine.mgm(ref, sec, dmin, dmax, default_params(algo, **kw), want_right=True)
     if name == "multi":      # half-pixel pass: see test_mgm_multi for why this one is held to the tolerance
         both = np.isfinite(g["disp"]) & np.isfinite(out["disp"])

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == _lib.exported_symbols(), "ctypes table and header disagree"
     for name in declared:
         assert hasattr(L, name), name
-    assert L.s2pb_version() == 100
+    assert L.s2pb_version() == 101
 
 
 def test_no_cpu_fallback():

@@ -18,11 +18,12 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 def test_port_matches_golden(oracle, name):
     ref, sec, dmin, dmax, kw = G.inputs(name)
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    kw = dict(kw)
-    if kw.pop("_algo", "mgm") == "mgm_multi":
-        d, c, dr = oracle.port.mgm_multi(ref, sec, dmin, dmax, oracle.mgm_multi_params(dct_shift=1, **kw))
+    algo, kw = G.split_kw(kw)
+    wl, wr = G.weights_for(name) or (None, None)
+    if algo == "mgm_multi":
+        d, c, dr = oracle.port.mgm_multi(ref, sec, dmin, dmax, oracle.mgm_multi_params(dct_shift=1, **kw), wl, wr)
     else:
-        d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(dct_shift=1, **kw))
+        d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(dct_shift=1, **kw), wl, wr)
     assert same(d, g["disp"]), "%d px differ" % nmismatch(d, g["disp"])
     assert np.array_equal(c.astype(np.uint8), g["conf"])
     assert same(dr, g["dispR"])
