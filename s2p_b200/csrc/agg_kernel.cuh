@@ -460,7 +460,9 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         // label loop and then added) was pinned against the binary: the P2 term of every neighbour and the P1 term
         // of the 3rd / 4th neighbour are fmas, the P1 term of the 1st / 2nd is mul + add (oracle/mgm_oracle.c,
         // orc_fma_mask).  With w = 1 all of these equal the unweighted x + P.
-        const float2 P1w = GEN ? __fmul2_rn(P1v, wv) : P1v;
+        // (scalar multiplies: ptxas fuses a packed mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2, which would
+        //  turn the mul + add of the 1st / 2nd neighbour into an fma)
+        const float2 P1w = GEN ? make_float2(__fmul_rn(P1, wv.x), __fmul_rn(P1, wv.y)) : P1v;
         auto qof = [&](const float2 m) { return GEN ? __ffma2_rn(P2v, wv, m) : __fadd2_rn(m, P2v); };
         const float2 qA = qof(mA), qB = qof(mB), qC = qof(mC), qE = qof(mE);
         const float2 nA = make_float2(-mA.x, -mA.y), nB = make_float2(-mB.x, -mB.y), nC = make_float2(-mC.x, -mC.y), nE = make_float2(-mE.x, -mE.y);
