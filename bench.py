@@ -39,11 +39,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--tiles", type=int, default=8, help="tiles per GPU per step")
+    ap.add_argument("--tiles", type=int, default=16, help="tiles per GPU per step")
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--dmin", type=int, default=-64)
     ap.add_argument("--dmax", type=int, default=63)
-    ap.add_argument("--slots", type=int, default=4, help="tiles in flight per GPU")
+    ap.add_argument("--slots", type=int, default=8, help="tiles in flight per GPU (one 8.5 GiB workspace each at the default shape)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="concurrent reference processes (0 = calibrate: all host cores, 1/2, 1/4)")
     ap.add_argument("--cpu-rows", type=int, default=32, help="rows of the CPU sample strips")
     ap.add_argument("--no-cpu", action="store_true")
@@ -212,19 +212,25 @@ def run_ours(a, rank, world, local_rank):
     streams = [torch.cuda.Stream(device=dev) for _ in range(nslots)]
     main = torch.cuda.current_stream(dev)
 
-    def device_step():
-        fork = torch.cuda.Event()
-        fork.record(main)
+    # The tile queue of a step is spread over `nslots` workspaces, each with its own stream; consecutive steps keep
+    # the queue full (a workspace's stream orders its own tiles), the streams are joined where the timed region ends.
+    def fork():
+        ev = torch.cuda.Event()
+        ev.record(main)
         for st in streams:
-            st.wait_event(fork)
+            st.wait_event(ev)
+
+    def join():
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+
+    def device_step():
         for t in range(B):
             sl = t % nslots
             eng.mgm_device(sl, d_ref[t].data_ptr(), d_sec[t].data_ptr(), W, H, a.dmin, a.dmax, p, d_disp[t].data_ptr(),
                            d_conf[t].data_ptr(), d_mask[t].data_ptr(), 0, nodata_hint=0, stream=streams[sl].cuda_stream)
-        for st in streams:
-            e = torch.cuda.Event()
-            e.record(st)
-            main.wait_event(e)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -242,20 +248,32 @@ def run_ours(a, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     # ---- device-resident arm
+    fork()
     for _ in range(max(3, a.warmup)):
         device_step()
+    join()
     barrier()
     l0 = eng.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
     e0.record(main)
+    fork()
     for _ in range(a.steps):
         device_step()
+    join()
     e1.record(main)
     barrier()
     tw1 = time.perf_counter()
     launches = eng.kernel_launches() - l0
     ms = max_over_ranks(e0.elapsed_time(e1))
+    # stage durations of the LAST tile of each workspace while the tiles overlap (diagnostic: how much the
+    # memory-bound WTA stretches when it shares the SMs with the next tile's aggregation)
+    overlapped = {}
+    try:
+        per_slot = [eng.last_timings(s) for s in range(len(streams))]
+        overlapped = {k: float(np.mean([t[k] for t in per_slot])) for k in per_slot[0]}
+    except Exception:
+        pass
     pix_step = world * B * W * H
     value = pix_step * a.steps / (ms * 1e-3) / 1e6
 
@@ -318,7 +336,7 @@ def run_ours(a, rank, world, local_rank):
                 "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read+write per launch)",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": agg,
                 "tile_ms_serial": float(np.mean(tot_ms[1:])), "stage_ms": stage,
-                "how": "serial single-tile launches after the timed region, CUDA events recorded by the library on the launching stream"}
+                "stage_ms_overlapped": overlapped, "how": "serial single-tile launches after the timed region, CUDA events recorded by the library on the launching stream"}
 
     clocks = None
     if sampler:

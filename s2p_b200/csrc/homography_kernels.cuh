@@ -89,6 +89,72 @@ __global__ void spline_columns_kernel(float *__restrict__ a, int w, int h, float
     }
 }
 
+// The same prefilter, one pole per launch, parallel ALONG the line as well: the poles are small (|z| = 0.43 and
+// 0.043), so the state of either recursion forgets its past at the rate |z|^k -- below 2e-12 after kSplineWarm = 32
+// samples, five orders of magnitude under float32 resolution.  A thread therefore owns kSplineSeg consecutive
+// samples of one column: it runs the forward recursion from a zero state kSplineWarm samples early (the first
+// segment starts from initForward's weighted sum instead, whose terms beyond 48 samples are below half an ulp),
+// keeps the forward values of its segment plus kSplineWarm more in registers, and runs the backward recursion from
+// a zero state that far beyond its end (the last segment from initBackward's exact start value).  w x (h / 64)
+// threads instead of w, and no global-memory latency chain: the 2250-column anti-aliasing case drops from 3.6 ms
+// per launch to tens of microseconds.  Out of place (in -> out); lines shorter than 2 * kSplineSeg use the
+// sequential kernel above.
+constexpr int kSplineSeg = 64, kSplineWarm = 32;
+__global__ void __launch_bounds__(128) spline_segments_kernel(const float *__restrict__ in, float *__restrict__ out, int w, int h,
+                                                             float scale, double pz)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const int s = blockIdx.y * kSplineSeg;
+    const int e = min(s + kSplineSeg, h);            // my samples: [s, e)
+    const int e2 = min(e + kSplineWarm, h);          // forward values kept for [s, e2)
+    const float zn = (float)pz;
+    const float *v = in + x;
+    const size_t st = (size_t)w;
+    float f[kSplineSeg + kSplineWarm];
+    float state;
+    if (s == 0) {            // initForward (Splines.cpp:315-340): v[0] + sum_k z^k v[k] (+ mirrored terms, < 1e-20 here)
+        double zk = pz;
+        state = v[0] * scale;
+        const int K = min(h - 2, 48);
+        for (int k = 1; k <= K; k++) { state = fmaf((float)zk, v[(size_t)k * st] * scale, state); zk *= pz; }
+    } else {                 // zero state kSplineWarm samples early, then the recursion proper
+        state = 0.f;
+#pragma unroll 8
+        for (int k = s - kSplineWarm; k < s; k++) state = fmaf(zn, state, v[(size_t)k * st] * scale);
+        state = fmaf(zn, state, v[(size_t)s * st] * scale);
+    }
+    f[0] = state;
+#pragma unroll
+    for (int q = 1; q < kSplineSeg + kSplineWarm; q++) {
+        if (s + q < e2) state = fmaf(zn, state, v[(size_t)(s + q) * st] * scale);
+        f[q] = state;
+    }
+    // backward: y[k] = z (y[k+1] - f[k]); exact start at the end of the line, zero state beyond an interior segment
+    float b;
+    float *o = out + x;
+    if (e2 == h) {
+        // initBackward (Splines.cpp:375-384) from the last two forward values
+        float last = 0.f, prev = 0.f;
+#pragma unroll
+        for (int q = 0; q < kSplineSeg + kSplineWarm; q++) { if (s + q == h - 1) last = f[q]; if (s + q == h - 2) prev = f[q]; }
+        b = (float)(pz / (pz * pz - 1.0)) * fmaf((float)pz, prev, last);
+        if (h - 1 < e) o[(size_t)(h - 1) * st] = b;
+#pragma unroll
+        for (int q = kSplineSeg + kSplineWarm - 1; q >= 0; q--) {
+            const int k = s + q;
+            if (k <= h - 2) { b = zn * (b - f[q]); if (k < e) o[(size_t)k * st] = b; }
+        }
+    } else {
+        b = 0.f;
+#pragma unroll
+        for (int q = kSplineSeg + kSplineWarm - 1; q >= 0; q--) {
+            b = zn * (b - f[q]);
+            if (q < kSplineSeg) o[(size_t)(s + q) * st] = b;      // s + q < e always holds for an interior segment
+        }
+    }
+}
+
 __device__ __forceinline__ float pow5f(float x) { float x2 = x * x; return x2 * x2 * x; }
 __device__ __forceinline__ void init_spline5(float w[6], float t)
 {   // Splines.cpp:215-227

@@ -1462,14 +1462,26 @@ static int map_image(s2pb_ctx *ctx, cudaStream_t st, const float *d_src, int w, 
     const double z0 = -0.430575, z1 = -0.0430963;
     nan_to_zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp.as<float>(), n);
     dim3 bt(32, 8);
+    // prefilter along x (on the transposed image) then along y; `a` holds the data, `b` is the other buffer
+    auto prefilter = [&](float *a, float *b, int lw, int lh) {      // columns of an lw x lh image, result back in a
+        if (lh >= 2 * kSplineSeg) {
+            dim3 g((lw + 127) / 128, (lh + kSplineSeg - 1) / kSplineSeg);
+            spline_segments_kernel<<<g, 128, 0, st>>>(a, b, lw, lh, lambda, z0);
+            spline_segments_kernel<<<g, 128, 0, st>>>(b, a, lw, lh, 1.f, z1);
+            ctx->launches += 2;
+        } else {
+            spline_columns_kernel<<<(lw + 31) / 32, 32, 0, st>>>(a, lw, lh, lambda, z0, z1);
+            ctx->launches++;
+        }
+    };
     transpose_kernel<<<dim3((tw + 31) / 32, (th + 31) / 32), bt, 0, st>>>(tmp.as<float>(), tw, th, scratch.as<float>());
-    spline_columns_kernel<<<(th + 31) / 32, 32, 0, st>>>(scratch.as<float>(), th, tw, lambda, z0, z1);      // rows of the image
+    prefilter(scratch.as<float>(), tmp.as<float>(), th, tw);                                                // rows of the image
     transpose_kernel<<<dim3((th + 31) / 32, (tw + 31) / 32), bt, 0, st>>>(scratch.as<float>(), th, tw, tmp.as<float>());
-    spline_columns_kernel<<<(tw + 31) / 32, 32, 0, st>>>(tmp.as<float>(), tw, th, lambda, z0, z1);
+    prefilter(tmp.as<float>(), scratch.as<float>(), tw, th);
     Mat9 Hi;
     invert33(useZ ? matZ : M, Hi.m);
     spline_warp_kernel<<<grid2d(ow, oh, b2), b2, 0, st>>>(tmp.as<float>(), tw, th, Hi, d_out, ow, oh);
-    ctx->launches += 6;
+    ctx->launches += 4;
     if (useZ) {
         Mat9 Ht;
         invert33(M, Ht.m);
