@@ -124,6 +124,7 @@ struct CostGenParams {
     const float *u, *v0, *v1;          // this view's image; matched image; matched image shifted by 1/2 px (ZOOMFACTOR 2)
     const uint64_t *cu, *cv0, *cv1;    // census codes of the same three (cost == census)
     const float *lut;                  // census: popcount -> cost (mgm_costvolume.h:90-91)
+    const float2 *su, *sv0, *sv1;      // ncc: per-pixel window (mean, variance) of the same three images (ncc_stats_kernel)
     const short *lo, *hi;
     int w, h, gmin, cost, win, zoom;
     float *C;
@@ -145,22 +146,34 @@ __device__ __forceinline__ float bt_cost(const float *__restrict__ u, const floa
     const float dRL = fmaxf(0.f, fmaxf(IR - ImaxL, IminL - IR));
     return fabsf(fminf(dLR, dRL));
 }
-__device__ __forceinline__ float ncc_cost(const float *__restrict__ u, const float *__restrict__ v, int w, int h, int x, int y, int qx, int hw)
-{   // computeC_clippedNCC, mgm_costvolume.h:152-180: window scanned x-major; any tap outside either image -> +INF
-    if (x - hw < 0 || x + hw >= w || qx - hw < 0 || qx + hw >= w || y - hw < 0 || y + hw >= h) return S2PB_INF;
-    float mu1 = 0.f, mu2 = 0.f, s1 = 0.f, s2 = 0.f, prod = 0.f;
-    for (int i = -hw; i <= hw; i++)
-        for (int j = -hw; j <= hw; j++) {
-            const size_t r = (size_t)(y + j) * w;
-            const float v1 = u[r + x + i], v2 = v[r + qx + i];
-            mu1 += v1; mu2 += v2;
-            s1 = fmaf(v1, v1, s1); s2 = fmaf(v2, v2, s2); prod = fmaf(v1, v2, prod);
-        }
-    const float n = (float)((2 * hw + 1) * (2 * hw + 1));
-    mu1 = __fdiv_rn(mu1, n); mu2 = __fdiv_rn(mu2, n);
-    s1 = __fdiv_rn(s1, n); s2 = __fdiv_rn(s2, n); prod = __fdiv_rn(prod, n);
-    const float num = fmaf(-mu1, mu2, prod);
-    const float den = fmaf(-mu1, mu1, s1) * fmaf(-mu2, mu2, s2);
+// computeC_clippedNCC, mgm_costvolume.h:152-180.  The window sums of one image (mu = sum v / n, s = sum v*v / n,
+// accumulated x-major with the reference build's fmas) depend on the pixel only, not on the label: they are computed
+// once per image by ncc_stats_kernel as (mu, s - mu*mu); the cost kernel is left with the cross term.
+__global__ void ncc_stats_kernel(const float *__restrict__ img, int w, int h, int hw, float2 *__restrict__ st)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float2 r = make_float2(0.f, 0.f);
+    if (x - hw >= 0 && x + hw < w && y - hw >= 0 && y + hw < h) {      // else: never read (the cost is +INF)
+        float mu = 0.f, s = 0.f;
+        for (int i = -hw; i <= hw; i++)
+            for (int j = -hw; j <= hw; j++) {
+                const float v = img[(size_t)(y + j) * w + x + i];
+                mu += v;
+                s = fmaf(v, v, s);
+            }
+        const float n = (float)((2 * hw + 1) * (2 * hw + 1));
+        mu = __fdiv_rn(mu, n);
+        s = __fdiv_rn(s, n);
+        r = make_float2(mu, fmaf(-mu, mu, s));
+    }
+    st[(size_t)y * w + x] = r;
+}
+__device__ __forceinline__ float ncc_finish(float prod, float n, float2 a, float2 b)
+{
+    prod = __fdiv_rn(prod, n);
+    const float num = fmaf(-a.x, b.x, prod);
+    const float den = a.y * b.y;
     const double dd = (0.0000001 > (double)den) ? 0.0000001 : (double)den;
     const float ncc = (float)((double)num / sqrt(dd));
     float cl = (ncc < 1.f) ? ncc : 1.f;
@@ -182,6 +195,43 @@ __global__ void cost_gen_kernel(const CostGenParams P)
         const int l = P.lo[p], hgh = P.hi[p];
         float c[LPL];
         bool anyfinite = false;
+        if (P.cost == kCostNCC) {
+            // cross term of every label of this lane at once: the taps run in the reference's order (x-major) for each
+            // label, the reference image's tap is loaded once per tap instead of once per tap and label
+            int q[LPL];
+            const float *vq[LPL];
+            bool ok[LPL];
+            const bool pin = x - hw >= 0 && x + hw < w && y - hw >= 0 && y + hw < P.h;
+#pragma unroll
+            for (int e = 0; e < LPL; e++) {
+                const int o = P.gmin + lane * LPL + e;
+                q[e] = x + o;
+                bool half = false;
+                if (P.zoom == 2) { q[e] = x + (o >> 1); half = (o & 1) != 0; }
+                vq[e] = half ? P.v1 : P.v0;
+                c[e] = S2PB_INF;
+                const bool inrange = o >= l && o <= hgh && q[e] >= 0 && q[e] < w;          // else the slot stays +INF
+                ok[e] = inrange && pin && q[e] - hw >= 0 && q[e] + hw < w;                  // else a tap is outside: +INF
+                if (ok[e]) c[e] = 0.f;
+            }
+            for (int i = -hw; i <= hw; i++)
+                for (int j = -hw; j <= hw; j++) {
+                    const size_t r = (size_t)(y + j) * w;
+                    const float ut = pin ? P.u[r + x + i] : 0.f;
+#pragma unroll
+                    for (int e = 0; e < LPL; e++)
+                        if (ok[e]) c[e] = fmaf(ut, vq[e][r + q[e] + i], c[e]);
+                }
+            const float n = (float)(P.win * P.win);
+            const float2 sa = pin ? P.su[p] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < LPL; e++)
+                if (ok[e]) {
+                    const float2 sb = (vq[e] == P.v1 ? P.sv1 : P.sv0)[row + q[e]];
+                    c[e] = ncc_finish(c[e], n, sa, sb);
+                    if (isfinite(c[e])) anyfinite = true;
+                }
+        } else
 #pragma unroll
         for (int e = 0; e < LPL; e++) {
             const int o = P.gmin + lane * LPL + e;
@@ -196,8 +246,7 @@ __global__ void cost_gen_kernel(const CostGenParams P)
                         val = P.lut[__popcll(P.cu[p] ^ codes[row + q])];
                     } else {
                         const float *v = half ? P.v1 : P.v0;
-                        if (P.cost == kCostNCC) val = ncc_cost(P.u, v, w, P.h, x, y, q, hw);
-                        else if (P.cost == kCostBTAD || P.cost == kCostBTSD) {
+                        if (P.cost == kCostBTAD || P.cost == kCostBTSD) {
                             const float b = bt_cost(P.u, v, w, row, x, q);
                             val = (P.cost == kCostBTAD) ? b : b * b;
                         } else {

@@ -599,6 +599,14 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
             if (census) { census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(shf[vi], w, h, p->census_win / 2, cen_half[vi]); ctx->launches++; }
         }
     }
+    const bool ncc = p->cost == S2PB_COST_NCC;       // window statistics live in the (then unused) census buffers: 8 B / pixel
+    if (ncc) {
+        for (int vi = 0; vi < 2; vi++) {
+            ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(img[vi], w, h, p->census_win / 2, (float2 *)s.v[vi].census);
+            ctx->launches++;
+            if (zoom == 2) { ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(shf[vi], w, h, p->census_win / 2, (float2 *)cen_half[vi]); ctx->launches++; }
+        }
+    }
     CK(cudaGetLastError());
     for (int vi = 0; vi < 2; vi++) {
         s.v[vi].lo = lo[vi]; s.v[vi].hi = hi[vi];
@@ -607,6 +615,7 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
             memset(&G, 0, sizeof G);
             G.u = img[vi]; G.v0 = img[1 - vi]; G.v1 = zoom == 2 ? shf[1 - vi] : nullptr;
             G.cu = s.v[vi].census; G.cv0 = s.v[1 - vi].census; G.cv1 = zoom == 2 ? cen_half[1 - vi] : nullptr;
+            G.su = (const float2 *)G.cu; G.sv0 = (const float2 *)G.cv0; G.sv1 = (const float2 *)G.cv1;
             G.lut = s.lut; G.lo = lo[vi]; G.hi = hi[vi];
             G.w = w; G.h = h; G.gmin = gminv[vi]; G.cost = p->cost; G.win = p->census_win; G.zoom = zoom;
             G.C = (float *)s.v[vi].C;
@@ -824,6 +833,10 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
         prepare_view_kernel<<<(n + 255) / 256, 256, 0, st>>>(im[vi], n, lo_all, hi_all, dmin, s.v[vi].img, s.v[vi].lo, s.v[vi].hi);
         ctx->launches++;
         if (census) { census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].img, w, h, p->census_win / 2, s.v[vi].census); ctx->launches++; }
+        if (p->cost == S2PB_COST_NCC) {     // window statistics in the (then unused) census buffer: 8 B / pixel
+            ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].img, w, h, p->census_win / 2, (float2 *)s.v[vi].census);
+            ctx->launches++;
+        }
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(s.ev[1], st));
@@ -834,6 +847,7 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
             memset(&G, 0, sizeof G);
             G.u = s.v[vi].img; G.v0 = s.v[1 - vi].img;
             G.cu = s.v[vi].census; G.cv0 = s.v[1 - vi].census;
+            G.su = (const float2 *)G.cu; G.sv0 = (const float2 *)G.cv0;
             G.lut = s.lut; G.lo = s.v[vi].lo; G.hi = s.v[vi].hi;
             G.w = w; G.h = h; G.gmin = gminv[vi]; G.cost = p->cost; G.win = p->census_win; G.zoom = 1;
             G.C = (float *)s.v[vi].C;
@@ -1200,9 +1214,16 @@ extern "C" int s2pb_costvolume_dist(s2pb_ctx *ctx, const float *u, const float *
         census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dv.as<float>(), w, h, win / 2, cv.as<uint64_t>());
         ctx->launches += 2;
     }
+    if (cost == S2PB_COST_NCC) {
+        dim3 b2(32, 8);
+        ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(du.as<float>(), w, h, win / 2, cu.as<float2>());
+        ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dv.as<float>(), w, h, win / 2, cv.as<float2>());
+        ctx->launches += 2;
+    }
     CostGenParams G;
     memset(&G, 0, sizeof G);
     G.u = du.as<float>(); G.v0 = dv.as<float>(); G.cu = cu.as<uint64_t>(); G.cv0 = cv.as<uint64_t>();
+    G.su = cu.as<float2>(); G.sv0 = cv.as<float2>();
     G.lut = dlut.as<float>(); G.lo = dlo.as<short>(); G.hi = dhi.as<short>();
     G.w = w; G.h = h; G.gmin = gmin; G.cost = cost; G.win = win; G.zoom = 1; G.C = dC.as<float>();
     rc = launch_cost_gen(ctx, LPL, G, st);
