@@ -52,11 +52,14 @@ def parse():
 
 def config(a, world):
     return {
-        "workload": "BASELINE configs[1]: single 1024x1024 rectified tile, disp_range=128, census5x5 + 8-path MGM "
-                    "(s2p algo 'mgm': TSGM=3, P1=8, P2=32, vfit, MEDIAN=1, LR check), %d tiles per GPU per step" % a.tiles,
+        "workload": "%ssingle %dx%d rectified tile, disp_range=%d, census5x5 + 8-path MGM "
+                    "(s2p algo 'mgm': TSGM=3, P1=8, P2=32, vfit, MEDIAN=1, LR check), %d tiles per GPU per step" % (
+                        "BASELINE configs[1]: " if (a.size, a.dmin, a.dmax) == (1024, -64, 63) else "", a.size, a.size,
+                        a.dmax - a.dmin + 1, a.tiles),
         "tile": [a.size, a.size], "dmin": a.dmin, "dmax": a.dmax, "labels": a.dmax - a.dmin + 1,
         "tiles_per_gpu_per_step": a.tiles, "tiles_in_flight": a.slots, "parallelism": "tile-shard x%d" % world,
-        "l2": "per-tile working set 8.5 GiB (8 float path volumes per view) >> 126 MB L2; inputs differ per tile",
+        "l2": "per-tile working set %.1f GiB (8 float path volumes per view) >> 126 MB L2; inputs differ per tile" % (
+            2 * 8 * 4.0 * a.size * a.size * (32 * ((a.dmax - a.dmin + 32) // 32)) / 2 ** 30 * 1.0625),
     }
 
 

@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_longlong, c_uint8, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libs2pb200.so")
+LIB_PATH = os.environ.get("S2PB200_LIB") or os.path.join(HERE, "libs2pb200.so")   # the override serves A/B kernel experiments
 
 OK, ERR_CUDA, ERR_ARG, ERR_TIMEOUT, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 T_NAMES = ("census", "cost", "aggregate", "wta", "post", "total")

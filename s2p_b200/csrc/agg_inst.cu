@@ -9,12 +9,13 @@ namespace s2pb {
 
 static constexpr int kLPL = S2PB_LPL;
 static constexpr size_t kSmem = AggSmem<kLPL, false>::bytes, kSmemGen = AggSmem<kLPL, true>::bytes;
-static constexpr int kCtaPerSm = (kLPL <= 4) ? 2 : 1;
 
 template <> int agg_configure_lpl<kLPL>()
 {
     cudaError_t e = cudaSuccess;
-#define CFG(T, S, G) e = cudaFuncSetAttribute(aggregate_kernel<kLPL, T, S, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(G ? kSmemGen : kSmem)); if (e) return -1;
+#define CFG(T, S, G) e = cudaFuncSetAttribute(aggregate_kernel<kLPL, T, S, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(G ? kSmemGen : kSmem)); if (e) return -1; \
+    if (kLPL > 4 && AggOcc<kLPL, T>::ctas == 2) { /* two CTAs of up to 113 KB: ask for the largest shared-memory carve-out */ \
+        e = cudaFuncSetAttribute(aggregate_kernel<kLPL, T, S, G>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared); if (e) return -1; }
     CFG(1, false, false) CFG(2, false, false) CFG(3, false, false) CFG(4, false, false)
     CFG(1, true, false) CFG(2, true, false) CFG(3, true, false) CFG(4, true, false)
     CFG(1, false, true) CFG(2, false, true) CFG(3, false, true) CFG(4, false, true)
@@ -25,12 +26,11 @@ template <> int agg_configure_lpl<kLPL>()
 template <> int agg_launch_lpl<kLPL>(int tsgm, const AggParams &P, int sm_count, cudaStream_t st)
 {
     // persistent CTAs, one (or two) per SM; bands are pulled from a global queue in dependency order
-    int grid = sm_count * kCtaPerSm;
-    int total = P.maxBands * P.nPV;
-    if (grid > total) grid = total;
+    const int total = P.maxBands * P.nPV;
     dim3 block(kAggThreads);
     const bool scaled = P.lut != nullptr;
-#define GO(T) do { if (P.general) aggregate_kernel<kLPL, T, false, true><<<grid, block, kSmemGen, st>>>(P); \
+#define GO(T) do { int grid = sm_count * AggOcc<kLPL, T>::ctas; if (grid > total) grid = total; \
+                   if (P.general) aggregate_kernel<kLPL, T, false, true><<<grid, block, kSmemGen, st>>>(P); \
                    else if (scaled) aggregate_kernel<kLPL, T, true, false><<<grid, block, kSmem, st>>>(P); \
                    else aggregate_kernel<kLPL, T, false, false><<<grid, block, kSmem, st>>>(P); } while (0)
     switch (tsgm) {

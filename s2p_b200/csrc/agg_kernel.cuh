@@ -37,7 +37,18 @@ constexpr int kMaxPV = 16;    // pass-views handled by one aggregation launch (2
 constexpr int kNW = 16;       // scanlines per band
 constexpr int kNWC = 8;       // warps per CTA, two scanlines each
 constexpr int kAggThreads = kNWC * 32;
-constexpr int kRing = 4;      // ring slots per compute warp for handing vectors to the next warp
+// One CTA barrier every SECOND pixel step (volumes of 5..8 labels per lane): consecutive warps are skewed by one
+// extra pixel, so that what a warp reads from its predecessor's ring was written two steps earlier and a barrier
+// after every odd step separates the two; the ring is 8 deep so that a slot is not reused within that slack.
+// Measured on B200: 8.47 -> 8.09 ms at 256 labels; at 128 labels (4 per lane) it is 2 % slower, so that
+// configuration keeps the barrier after every step.
+#ifndef S2PB_SYNC2
+#define S2PB_SYNC2 1
+#endif
+template <int LPL> struct SyncCfg {
+    static constexpr bool sync2 = S2PB_SYNC2 && LPL > 4 && LPL <= 8;
+    static constexpr int kRing = sync2 ? 8 : 4;      // ring slots per compute warp for handing vectors to the next warp
+};
 constexpr int kPublish = 8;   // a band publishes its progress every kPublish pixels
 
 // ------------------------------------------------------------------ small helpers
@@ -295,6 +306,7 @@ template <int LPL, bool GEN = false> struct AggSmem {
     static constexpr int DP = 32 * LPL;
     static constexpr int kStage = StageCfg<LPL, GEN>::kStage, kR0 = StageCfg<LPL, GEN>::kR0;
     static constexpr size_t kCostBytes = GEN ? sizeof(float) : sizeof(__half);
+    static constexpr int kRing = SyncCfg<LPL>::kRing;
     static constexpr size_t ring_off = 0;                                            // float [kNWC][kRing][DP]
     static constexpr size_t ringm_off = ring_off + sizeof(float) * kNWC * kRing * DP; // float [kNWC][kRing]
     static constexpr size_t r0_off = ringm_off + sizeof(float) * kNWC * kRing;        // float [kR0][DP]   previous band
@@ -338,12 +350,14 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     constexpr int U = useE ? 3 : 2;       // window / history registers rotate with period U: the step loop is unrolled by U
     using SM = AggSmem<LPL, GEN>;
     using CT = typename std::conditional<GEN, float, __half>::type;      // stored cost element
-    constexpr int kStage = SM::kStage, kR0 = SM::kR0, S = kStage - 1;
+    constexpr int kStage = SM::kStage, kR0 = SM::kR0, S = kStage - 1, kRing = SM::kRing;
+    constexpr bool SYNC2 = SyncCfg<LPL>::sync2;
+    constexpr int WSK = SYNC2 ? 2 * SKEW + 1 : 2 * SKEW;   // pixels by which a warp's upper scanline trails the previous warp's
     constexpr int CB = DP * (int)sizeof(CT);   // bytes of one pixel's cost vector
     constexpr int CH = CB / 16;                // ... in 16-byte chunks
 
     const int nI = pd.nI;
-    const int nsteps = (nI + (kNW - 1) * SKEW + U - 1) / U * U;
+    const int nsteps = (nI + (kNWC - 1) * WSK + SKEW + U - 1) / U * U;
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
 
     // ---- this warp's two scanlines: A (upper) and B = A + 1
@@ -534,7 +548,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     // end-of-line predicate from the step; the slow variant handles ramp-up, ramp-down and the image border.
     auto step = [&](auto fast_c, const int t, NbVec<LPL> &xB, NbVec<LPL> &xC, NbVec<LPL> &xE, NbVec<LPL> &hNew, NbVec<LPL> &hC, NbVec<LPL> &hE) {
         constexpr bool FAST = decltype(fast_c)::value;
-        const int iA = t - 2 * k * SKEW, iB = iA - SKEW;
+        const int iA = t - k * WSK, iB = iA - SKEW;
         const bool actA = FAST || (liveA && iA >= 0 && iA < nI), actB = FAST || (liveB && iB >= 0 && iB < nI);
         NbVec<LPL> &inlineA = useE ? hE : hC;                 // A's result of the previous step
         if (FAST || iA - rsel * SKEW >= 0) stage_cost();      // my scanline is at pixel jc - S: stage pixel jc
@@ -587,11 +601,12 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
                 }
             }
         }
-        __syncthreads();
+        if (!SYNC2 || (t & 1)) __syncthreads();
+        else __syncwarp();      // the staging slot the lanes just read is overwritten by the next step's cp.async
     };
     // a step is FAST for this warp when A is at an interior pixel with B one SKEW behind, also interior
     const bool can_fast = liveA && liveB && prevA;
-    const int fast_lo = 2 * k * SKEW + SKEW + 1, fast_hi = 2 * k * SKEW + nI - 2;     // t range: iB >= 1 and iA <= nI-2
+    const int fast_lo = k * WSK + SKEW + 1, fast_hi = k * WSK + nI - 2;     // t range: iB >= 1 and iA <= nI-2
     auto do_step = [&](const int t, NbVec<LPL> &xB, NbVec<LPL> &xC, NbVec<LPL> &xE, NbVec<LPL> &hNew, NbVec<LPL> &hC, NbVec<LPL> &hE) {
         if (can_fast && t >= fast_lo && t <= fast_hi) step(std::true_type{}, t, xB, xC, xE, hNew, hC, hE);
         else step(std::false_type{}, t, xB, xC, xE, hNew, hC, hE);
@@ -610,8 +625,20 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     cp_async_wait<0>();
 }
 
+// Register cap and resident CTAs per SM.  Up to 4 labels per lane two CTAs fit at 112 registers; for 5..8 labels per
+// lane (160..256 labels) a cap of 128 registers still holds two CTAs (8 x 32 x 128 x 2 = the whole register file)
+// with no or few spills, which doubles the warps available to hide the lock-step latency; the 4-neighbour recursion
+// at 8 labels per lane and the widest volumes keep one CTA with all the registers they want.
+#ifndef S2PB_WIDE_TWO_CTAS
+#define S2PB_WIDE_TWO_CTAS 0   /* measured on B200: 6.9 -> 6.4 ms alone at 192 labels, but 115 -> 94 Mpix/s with tiles in flight (no room left for the WTA CTAs) */
+#endif
+template <int LPL, int TSGM> struct AggOcc {
+    static constexpr bool two_wide = S2PB_WIDE_TWO_CTAS && (LPL <= 6 || (LPL == 8 && TSGM <= 3));
+    static constexpr int regs = (LPL <= 4) ? 112 : (two_wide ? 128 : 255);
+    static constexpr int ctas = (regs <= 128) ? 2 : 1;
+};
 template <int LPL, int TSGM, bool SCALED, bool GEN>
-__global__ void __launch_bounds__(kAggThreads) __maxnreg__((LPL <= 4) ? 112 : 255) aggregate_kernel(const __grid_constant__ AggParams P)
+__global__ void __launch_bounds__(kAggThreads) __maxnreg__((AggOcc<LPL, TSGM>::regs)) aggregate_kernel(const __grid_constant__ AggParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_item;
