@@ -11,6 +11,11 @@ eng = Engine(0)
 ref, sec, _ = make_pair(1024, 1024, -64, 63, seed=0)
 for _ in range(2):
     out = eng.mgm(ref, sec, -64, 63, default_params("mgm"))
+# general flavour: another distance, NCC, census with -wl / -wr weights
+wl = np.maximum(np.random.default_rng(1).uniform(0, 1, ref.shape) ** 2, 0.1).astype(np.float32)
+eng.mgm(ref, sec, -64, 63, default_params("mgm", cost="btad"))
+eng.mgm(ref, sec, -64, 63, default_params("mgm", cost="ncc"))
+eng.mgm(ref, sec, -64, 63, default_params("mgm"), weights=(wl, wl))
 r3, s3, _ = make_pair(532, 768, -128, 127, seed=5)
 for _ in range(2):
     eng.mgm(r3, s3, -128, 127, default_params("mgm_multi"))
