@@ -39,8 +39,29 @@ def test_default_params_mirror_s2p_flags():
     assert (p.P1, p.P2, p.lr_mode, p.lr_tau, p.mindiff, p.remove_small_cc) == (8.0, 32.0, 1, 1.0, -1.0, 0)
     q = default_params("mgm_multi")      # s2p/block_matching.py:269-308
     assert (q.tsgm, q.median, q.scales, q.subpix, q.remove_small_cc) == (4, 0, 6, 2, 25)
+    r = default_params("mgm_multi_lsd")  # s2p/block_matching.py:191-266: P1 = 12, P2 = 48, MEDIAN = 1, SUBPIX = 2, -S 6
+    assert (r.tsgm, r.median, r.scales, r.subpix, r.remove_small_cc, r.P1, r.P2, r.cost) == (4, 1, 6, 2, 25, 12.0, 48.0, 0)
+    assert default_params("mgm", cost="ncc").cost == 3 and default_params("mgm", cost=4).cost == 4
+    with pytest.raises(ValueError):
+        default_params("mgm", cost="l1")
     with pytest.raises(Exception):
         default_params("sgbm")
+
+
+def test_params_struct_matches_the_header():
+    """ctypes mirror and C struct must agree field for field (order, width): parse the header's struct."""
+    import ctypes
+    import re
+    from s2p_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "s2pb200.h")).read()
+    body = re.search(r"typedef struct s2pb_mgm_params \{(.*?)\} s2pb_mgm_params;", src, re.S).group(1)
+    fields = re.findall(r"^\s*(int32_t|float)\s+(\w+);", body, re.M)
+    assert [n for _, n in fields] == [n for n, _ in _lib.MgmParams._fields_]
+    assert [t for t, _ in fields] == ["int32_t" if t is ctypes.c_int32 else "float" for _, t in _lib.MgmParams._fields_]
+    assert ctypes.sizeof(_lib.MgmParams) == 4 * len(fields)
+    enum = re.search(r"enum \{ (S2PB_COST_CENSUS.*?)\};", src, re.S).group(1)
+    names = [x.strip().split(" ")[0] for x in enum.split(",") if x.strip()]
+    assert [n[len("S2PB_COST_"):].lower() for n in names[:-1]] == list(_lib.COSTS) and names[-1] == "S2PB_COST_COUNT"
 
 
 def test_disparity_bounds_and_errors():
@@ -51,6 +72,7 @@ def test_disparity_bounds_and_errors():
     with pytest.raises(bm.MaxDisparityRangeError):                    # tests/block_matching_test.py:23-36 in the reference
         bm.disparity_bounds(1024, -100, 100, max_disp_range=10)
     assert bm.confidence_path("/x/rectified_disp.tif") == "/x/rectified_disp_confidence.tif"
+    assert bm.confidence_path("/x/rectified_disp.tif", "mgm_multi_lsd") == "/x/rectified_disp.tif.confidence.tif"   # :238
     with pytest.raises(NotImplementedError):
         bm.compute_disparity_map("a", "b", "c", "d", "sgbm")
 
@@ -66,6 +88,8 @@ def test_matcher_params_follow_cfg():
         assert (p.census_win, p.ndir, p.lr_tau, p.P1, p.P2, p.timeout_ms) == (3, 4, 2.0, 8.0, 32.0, 600000)
         q = bm.matcher_params("mgm_multi", 5)
         assert (q.P1, q.P2, q.remove_small_cc, q.timeout_ms) == (16.0, 64.0, 7, 5000)
+        r = bm.matcher_params("mgm_multi_lsd", 0)
+        assert (r.P1, r.P2, r.remove_small_cc, r.median, r.timeout_ms) == (24.0, 96.0, 7, 1, 0)
     finally:
         cfg.clear()
         cfg.update(old)

@@ -106,3 +106,62 @@ def test_reference_sample_pair(oracle):
     r = oracle.run_ref(a, b, -22, 19, P)
     d, c, dr = oracle.port.mgm(a, b, -22, 19, P)
     assert same(d, r["disp"]) and same(c, r["conf"]) and same(dr, r["dispR"])
+
+
+def _lsd_like_weights(shape, seed, ones=0.6):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 255, shape)
+    w = np.maximum(((255 - x) / 255) ** 2, 0.1).astype(np.float32)
+    w[rng.random(shape) < ones] = 1.0
+    return w
+
+
+@pytest.mark.parametrize("cost,kw", [(1, {}), (2, {"tsgm": 4}), (3, {"census_win": 3}), (3, {}), (3, {"census_win": 7}), (4, {}), (5, {"ndir": 4})])
+def test_port_distances_match_reference_binary(oracle, cost, kw):
+    """-t ad | sd | ncc | btad | btsd (mgm_costvolume.h:186-197), NaN-free and with no-data strips"""
+    if not _have_ref(oracle):
+        pytest.skip("oracle/_ref/mgm not built (needs /root/reference)")
+    from s2p_b200.synth import make_pair
+    h, w, dmin, dmax = 40, 66, -9, 8
+    for nanb in (0.0, 0.06):
+        ref, sec, _ = make_pair(h, w, dmin, dmax, seed=61 + cost, nan_border=nanb)
+        P = oracle.mgm_params(dct_shift=1, cost=cost, **kw)
+        r = oracle.run_ref(ref, sec, dmin, dmax, P, threads=1)
+        d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, P)
+        assert same(d, r["disp"]), "%d px differ" % nmismatch(d, r["disp"])
+        assert same(c, r["conf"]) and same(dr, r["dispR"])
+
+
+@pytest.mark.parametrize("kw", [dict(tsgm=1), dict(tsgm=2), dict(tsgm=3), dict(tsgm=4), dict(tsgm=4, ndir=4), dict(tsgm=3, cost=1),
+                                dict(tsgm=3, P1=7.0, P2=33.3)])
+def test_port_weights_match_reference_binary(oracle, kw):
+    """-wl / -wr with penalties whose products with the weights are inexact: pins how the reference build rounds
+    x + P*w for each of the four neighbours (orc_fma_mask in oracle/mgm_oracle.c)"""
+    if not _have_ref(oracle):
+        pytest.skip("oracle/_ref/mgm not built (needs /root/reference)")
+    from s2p_b200.synth import make_pair
+    h, w, dmin, dmax = 48, 70, -10, 9
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=71)
+    wl, wr = _lsd_like_weights((h, w), 1), _lsd_like_weights((h, w), 2, 0.3)
+    kw = dict(dict(P1=12.0, P2=48.0), **kw)
+    P = oracle.mgm_params(dct_shift=1, **kw)
+    r = oracle.run_ref(ref, sec, dmin, dmax, P, threads=1, wl=wl, wr=wr)
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, P, wl, wr)
+    assert same(d, r["disp"]), "%d px differ" % nmismatch(d, r["disp"])
+    assert same(c, r["conf"]) and same(dr, r["dispR"])
+
+
+@pytest.mark.parametrize("kw,weighted", [(dict(P1=12.0, P2=48.0, median=1), True), (dict(cost=1), False), (dict(cost=3, subpix=1), False)])
+def test_port_mgm_multi_options_match_reference_binary(oracle, kw, weighted):
+    """what algo == 'mgm_multi_lsd' runs, and mgm_multi with another distance (half-pixel pass on the images)"""
+    if not _have_ref(oracle):
+        pytest.skip("oracle/_ref/mgm_multi not built (needs /root/reference)")
+    from s2p_b200.synth import make_pair
+    h, w, dmin, dmax = 112, 140, -14, 17
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=81)
+    wl, wr = (_lsd_like_weights((h, w), 3, 0.7), _lsd_like_weights((h, w), 4, 0.7)) if weighted else (None, None)
+    P = oracle.mgm_multi_params(dct_shift=1, **kw)
+    r = oracle.run_ref(ref, sec, dmin, dmax, P, threads=1, wl=wl, wr=wr)
+    d, c, dr = oracle.port.mgm_multi(ref, sec, dmin, dmax, P, wl, wr)
+    assert same(d, r["disp"]), "%d px differ" % nmismatch(d, r["disp"])
+    assert same(c, r["conf"]) and same(dr, r["dispR"])
