@@ -88,7 +88,10 @@ int          s2pb_default_params(const char *algo, s2pb_mgm_params *p);
 
 /* ---- the matcher ----------------------------------------------------------- */
 /* Host buffers in, host buffers out (H2D/D2H inside).  disp, conf: w*h float32;
- * mask: w*h uint8 (0 rejected / 1 accepted) or NULL; disp_right: w*h or NULL. */
+ * mask: w*h uint8 (0 rejected / 1 accepted) or NULL; disp_right: w*h or NULL.
+ * Buffers may be pageable or page-locked (cudaHostAlloc / cudaHostRegister): page-locked
+ * ones are used for the DMA directly, pageable ones are staged through the library's own
+ * pinned block. */
 int s2pb_mgm(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h,
              int dmin, int dmax, const s2pb_mgm_params *p,
              float *disp, float *conf, uint8_t *mask, float *disp_right);
@@ -116,7 +119,8 @@ int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, const float *d_
                     int nodata_hint, void *stream);
 
 /* n independent tiles of identical shape, pipelined over the context's slots
- * (pinned staging + H2D, compute, D2H overlap).  Arrays of n host pointers. */
+ * (staging or direct DMA as above, H2D / compute / D2H of different tiles overlap).
+ * Arrays of n host pointers. */
 int s2pb_mgm_batch(s2pb_ctx *ctx, int n, const float *const *im1, const float *const *im2,
                    int w, int h, int dmin, int dmax, const s2pb_mgm_params *p,
                    float *const *disp, float *const *conf, uint8_t *const *mask);
