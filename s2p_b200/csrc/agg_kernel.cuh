@@ -212,7 +212,8 @@ struct AggParams {
 };
 
 // cp.async pipeline depth in pixel steps (kStage) and slots of the previous-band ring (kR0 > kStage + 1,
-// because pixel 0 is staged ahead of the pipeline); shallower for the widest volumes so the CTA fits 227 KB
+// because pixel 0 is staged ahead of the pipeline); shallower for the widest volumes.  (16 labels per lane would
+// still fit 227 KB with 8 stages, but measured no faster: 32.7 vs 31.9 ms on the C3-like mgm_multi tile.)
 template <int LPL, bool GEN = false> struct StageCfg {
     static constexpr int kStage = GEN ? ((LPL <= 4) ? 8 : (LPL <= 8) ? 4 : 2) : ((LPL <= 12) ? 8 : 2);
     static constexpr int kR0 = 2 * kStage;

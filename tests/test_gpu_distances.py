@@ -74,6 +74,25 @@ def test_mgm_distances(engine, oracle, cost, kw):
     assert same(out["disp_right"], dr)
 
 
+@pytest.mark.parametrize("shape,dmin,dmax,cost,weighted", [
+    ((30, 200), -90, 70, "ad", False),      # D=161 -> 6 labels per lane, barrier every second step
+    ((24, 260), -128, 127, "btad", True),   # D=256 -> 8
+    ((20, 400), -150, 150, "census", True), # D=301 -> 12
+    ((18, 520), -250, 249, "sd", True),     # D=500 -> 16
+])
+def test_general_flavour_wide_volumes(engine, oracle, shape, dmin, dmax, cost, weighted):
+    from s2p_b200.engine import default_params
+    h, w = shape
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=91)
+    wts = (_weights((h, w), 7), _weights((h, w), 8)) if weighted else None
+    out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm", cost=cost, P1=12.0, P2=48.0), want_right=True, weights=wts)
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(cost=oracle.COSTS.index(cost), P1=12.0, P2=48.0),
+                               *(wts or (None, None)))
+    assert same(out["disp"], d), "disparity differs at %d px" % nmismatch(out["disp"], d)
+    assert same(out["conf"], c)
+    assert same(out["disp_right"], dr)
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(P1=12.0, P2=48.0), dict(P1=12.0, P2=48.0, tsgm=4), dict(P1=5.5, P2=41.0, tsgm=2, ndir=4),
                                 dict(P1=12.0, P2=48.0, cost="ad"), dict(census_win=7, P1=12.0, P2=48.0)])
 def test_mgm_weighted(engine, oracle, kw):

@@ -61,6 +61,8 @@ def test_aggregate(engine, oracle, tsgm, ndir):
     ((30, 200), -90, 70, 0.0, 5),     # D=161 -> 6
     ((24, 260), -128, 127, 0.0, 6),   # D=256 -> 8
     ((70, 45), 3, 19, 0.05, 7),       # positive range, more rows than columns, no-data
+    ((20, 400), -150, 150, 0.0, 8),   # D=301 -> 12
+    ((18, 520), -250, 249, 0.03, 9),  # D=500 -> 16 (the widest slab)
 ])
 def test_mgm_end_to_end(engine, oracle, shape, dmin, dmax, nanb, seed):
     h, w = shape
