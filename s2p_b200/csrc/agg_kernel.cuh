@@ -15,7 +15,9 @@
 //   L_p     f32  [H][W][DP]   one volume per scan pass p (kept separate so that the
 //                             passes run concurrently and are still summed in the
 //                             reference's 1-thread order 0..7)
-//   Lmin_p  f32  [H][W], arg_p i16 [H][W]   per-pass minimum and LAST arg-minimum
+//   Lmin_p  f32  [H][W]       per-pass vector minimum; only the band-closing scanlines are written (the next band
+//                             reads them back); the per-pass LAST arg-minimum for the consensus is recomputed by the
+//                             WTA kernel from L_p
 // DP = 32*LPL slots per pixel (LPL labels per lane); a warp owns one pixel, lane l owns
 // slots [l*LPL, (l+1)*LPL), so every access to a pixel's vector is one fully coalesced
 // 64*LPL- or 128*LPL-byte request whatever the scan direction of the pass.
