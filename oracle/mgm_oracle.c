@@ -412,7 +412,8 @@ static void vfit(const float v[3], float *vmin, float *xmin)
     float slope = v[2] - v[1];
     if ((v[2] - v[1]) < (v[0] - v[1])) slope = v[0] - v[1];
     *xmin = (v[0] - v[2]) / (2 * slope);
-    *vmin = v[2] + (*xmin - 1) * slope;
+    *vmin = fmaf(*xmin - 1, slope, v[2]);   /* `v[2] + (xmin - 1) * slope`: one fma in the reference build (pinned by the
+                                               MINDIFF cases of scripts/fuzz_oracle.py: the cost image feeds mindiff's argmin) */
 }
 static void parabola(const float v[3], float *vmin, float *xmin)
 {   /* refine.h:40-68 */
@@ -423,7 +424,7 @@ static void parabola(const float v[3], float *vmin, float *xmin)
     float x = -b / (2 * a);
     if (x > 1) x = 1;
     if (x < -1) x = -1;
-    *vmin = (a * x + b) * x + c;
+    *vmin = fmaf(fmaf(a, x, b), x, c);      /* `(a*x + b)*x + c`: two fmas in the reference build */
     *xmin = x;
 }
 

@@ -324,7 +324,7 @@ __device__ __forceinline__ void vfit3(float v0, float v1, float v2, float &vmin,
     float slope = v2 - v1;
     if ((v2 - v1) < (v0 - v1)) slope = v0 - v1;
     xmin = __fdiv_rn(v0 - v2, 2.f * slope);
-    vmin = v2 + (xmin - 1.f) * slope;
+    vmin = fmaf(xmin - 1.f, slope, v2);     // one fma in the reference build (pinned: oracle/mgm_oracle.c, scripts/fuzz_oracle.py)
 }
 __device__ __forceinline__ void parabola3(float v0, float v1, float v2, float &vmin, float &xmin)
 {   // refine.h:40-68
@@ -335,7 +335,7 @@ __device__ __forceinline__ void parabola3(float v0, float v1, float v2, float &v
     float x = __fdiv_rn(-b, 2.f * a);
     if (x > 1.f) x = 1.f;
     if (x < -1.f) x = -1.f;
-    vmin = (a * x + b) * x + c;
+    vmin = fmaf(fmaf(a, x, b), x, c);       // two fmas in the reference build
     xmin = x;
 }
 
