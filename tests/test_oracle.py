@@ -2,6 +2,7 @@
 (outputs of the unmodified reference binary) and, when oracle/_ref is present, against that binary
 run live.  Bit-exact."""
 import os
+import subprocess
 import sys
 
 import numpy as np
@@ -165,3 +166,15 @@ def test_port_mgm_multi_options_match_reference_binary(oracle, kw, weighted):
     d, c, dr = oracle.port.mgm_multi(ref, sec, dmin, dmax, P, wl, wr)
     assert same(d, r["disp"]), "%d px differ" % nmismatch(d, r["disp"])
     assert same(c, r["conf"]) and same(dr, r["dispR"])
+
+
+def test_fuzz_sample_against_reference_binary(oracle):
+    """A fixed sample of scripts/fuzz_oracle.py (random shapes, ranges, every parameter incl. MINDIFF, distances,
+    weights, mgm and mgm_multi): the port must equal the binary on all of them."""
+    if not _have_ref(oracle):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_oracle.py"), "24", "7"], capture_output=True, text=True,
+                       timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "done: 24 cases, 0 with a mismatch" in r.stdout, r.stdout[-2000:]
