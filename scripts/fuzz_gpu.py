@@ -48,7 +48,9 @@ for it in range(N):
     P = (O.mgm_multi_params if multi else O.mgm_params)(**kw)
     d, c, dr = (O.port.mgm_multi if multi else O.port.mgm)(ref, sec, dmin, dmax, P, *(wts or (None, None)))
     try:
-        out = eng.mgm(ref, sec, dmin, dmax, default_params("mgm_multi" if multi else "mgm", **kw), want_right=True, weights=wts)
+        # timeout_ms: a deadlocked persistent kernel is drained through the abort flag instead of hanging the box
+        out = eng.mgm(ref, sec, dmin, dmax, default_params("mgm_multi" if multi else "mgm", timeout_ms=20000, **kw), want_right=True,
+                      weights=wts)
     except Exception as e:
         print(it, "engine refused:", e, (h, w), dmin, dmax, kw, flush=True)
         continue
