@@ -92,6 +92,16 @@ def lsd_weight_map(im):
             os.remove(out)
 
 
+def _original_compute_disparity_map():
+    """s2p's own implementation (the one install() replaced, if it did), or None when s2p is not importable."""
+    try:
+        from s2p import block_matching as original  # pragma: no cover
+    except Exception:
+        return None
+    fn = getattr(original, "_s2pb_original_compute_disparity_map", original.compute_disparity_map)
+    return None if fn is compute_disparity_map else fn
+
+
 def compute_disparity_map(im1, im2, disp, mask, algo, disp_min=None, disp_max=None, timeout=600,
                           max_disp_range=None, extra_params=""):
     """Same contract as s2p.block_matching.compute_disparity_map (see the module docstring).
@@ -100,12 +110,10 @@ def compute_disparity_map(im1, im2, disp, mask, algo, disp_min=None, disp_max=No
     ``common.run(timeout=)`` does for the mgm binaries) or subprocess.CalledProcessError.
     """
     if algo not in _NATIVE:
-        try:
-            from s2p import block_matching as original  # pragma: no cover
-        except Exception as e:
+        fn = _original_compute_disparity_map()
+        if fn is None:
             raise NotImplementedError("algo %r is not served by the B200 engine and the s2p package "
-                                      "is not importable to fall through to" % algo) from e
-        fn = getattr(original, "_s2pb_original_compute_disparity_map", original.compute_disparity_map)
+                                      "is not importable to fall through to" % algo)
         return fn(im1, im2, disp, mask, algo, disp_min, disp_max, timeout, max_disp_range, extra_params)
 
     width, _ = rio.image_size(im1)
@@ -125,6 +133,7 @@ def compute_disparity_map(im1, im2, disp, mask, algo, disp_min=None, disp_max=No
     except S2pbError as e:
         if e.code == _lib.ERR_TIMEOUT:
             raise subprocess.TimeoutExpired(cmd, timeout) from e
+        # everything else (no device, a shape the engine does not serve, ...) fails loudly: there is no CPU path
         raise subprocess.CalledProcessError(-e.code, cmd, output=str(e)) from e
     rio.write_float_tiff(disp, out["disp"])
     rio.write_float_tiff(confidence_path(disp, algo), out["conf"])
