@@ -540,6 +540,16 @@ static void orc_view(const float *u, const float *v, int w, int h, const float *
     int npix = w * h;
     int *lo = malloc(sizeof(int) * npix), *hi = malloc(sizeof(int) * npix);
     orc_ranges(dminI, dmaxI, npix, zoom, lo, hi);
+    {   /* analysis hook (scripts/range_width_analysis.py): dump the per-pixel label ranges of every mgm_call */
+        const char *dp = getenv("ORC_DUMP_RANGES");
+        if (dp) {
+            static int cnt = 0;
+            char fn[512];
+            snprintf(fn, sizeof fn, "%s/ranges_%03d_z%d_%dx%d.bin", dp, cnt++, zoom, w, h);
+            FILE *f = fopen(fn, "wb");
+            if (f) { fwrite(lo, sizeof(int), npix, f); fwrite(hi, sizeof(int), npix, f); fclose(f); }
+        }
+    }
     int gmin = lo[0], gmax = hi[0];
     for (int i = 1; i < npix; i++) { if (lo[i] < gmin) gmin = lo[i]; if (hi[i] > gmax) gmax = hi[i]; }
     int D = gmax - gmin + 1;
