@@ -9,4 +9,8 @@ template <int LPL> int agg_launch_lpl(int tsgm, const AggParams &P, int sm_count
 template <int LPL> int agg_configure_lpl();
 int agg_configure();                                   // 0 ok
 int agg_launch(int LPL, int tsgm, const AggParams &P, int sm_count, cudaStream_t st);   // 0 ok, -1 CUDA error, -2 unsupported
+// experimental chunk-skipping aggregation (agg_chunked.cuh); -2 = shape not served, use the dense kernel
+struct ChunkedParams;
+int agg_chunked_configure();
+int agg_chunked_launch(int tsgm, const ChunkedParams &P, int sm_count, cudaStream_t st);
 }  // namespace s2pb

@@ -11,6 +11,7 @@
 #include "fusion_kernels.cuh"
 #include "triangulation_kernels.cuh"
 #include "agg_dispatch.h"
+#include "agg_chunked.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -389,9 +390,15 @@ static void fill_pass(PassDesc &pd, int pass, int w, int h)
 }
 
 // Enqueue the 8-pass aggregation of `nviews` views of slot s in ONE persistent launch.
+// S2PB_CHUNKED=1 in the environment routes the f16-cost aggregation of mgm_multi's levels to the experimental
+// chunk-skipping kernel (agg_chunked.cuh)
+static bool chunked_enabled() { static int v = -1; if (v < 0) { const char *e = getenv("S2PB_CHUNKED"); v = e ? atoi(e) != 0 : 0; } return v != 0; }
+
 // general: the float-cost flavour; wgt[vi] = that view's weight image or nullptr (general only)
+// gminv: label of slot 0 per view (only needed by the chunk-skipping kernel; nullptr = dense kernel)
 static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, int LPL, float P1, float P2, int ndir, int tsgm,
-                            const float *lut, cudaStream_t st, bool general = false, const float *const *wgt = nullptr)
+                            const float *lut, cudaStream_t st, bool general = false, const float *const *wgt = nullptr,
+                            const int *gminv = nullptr)
 {
     AggParams P;
     memset(&P, 0, sizeof P);
@@ -411,6 +418,20 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
     P.P1 = P1; P.P2 = P2; P.next_item = s.next_item; P.abort_flag = ctx->abort_flag; P.lut = general ? nullptr : lut;
     P.general = general ? 1 : 0;
     CK(cudaMemsetAsync(s.next_item, 0, 4, st));
+    if (!general && gminv && chunked_enabled()) {
+        ChunkedParams Q;
+        memset(&Q, 0, sizeof Q);
+        Q.A = P;
+        Q.DP = 32 * LPL;
+        int q = 0;
+        for (int vi = 0; vi < nviews; vi++)
+            for (int p = 0; p < ndir; p++, q++) { Q.lo[q] = s.v[vi].lo; Q.hi[q] = s.v[vi].hi; Q.gmin[q] = gminv[vi]; }
+        static bool configured = false;
+        if (!configured) { if (agg_chunked_configure() != 0) return fail(S2PB_ERR_CUDA, "chunked aggregation: cudaFuncSetAttribute failed"); configured = true; }
+        int rr = agg_chunked_launch(tsgm, Q, ctx->sm_count, st);
+        if (rr == 0) { ctx->launches++; return S2PB_OK; }
+        if (rr != -2) return fail(S2PB_ERR_CUDA, "chunked aggregation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     int r = agg_launch(LPL, tsgm, P, ctx->sm_count, st);
     if (r == -2) return fail(S2PB_ERR_UNSUPPORTED, "no aggregation kernel for %d labels per lane", LPL);
     if (r != 0) return fail(S2PB_ERR_CUDA, "aggregation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -635,7 +656,7 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
         if (rc != S2PB_OK) return rc;
     }
     TRACE(st, "  census + cost");
-    rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1 / (float)zoom, p->P2, p->ndir, p->tsgm, lut, st, general, wgt);   // mgm_multiscale.cc:194-202
+    rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1 / (float)zoom, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, gminv);   // mgm_multiscale.cc:194-202
     if (rc != S2PB_OK) return rc;
     TRACE(st, "  aggregate");
     for (int vi = 0; vi < 2; vi++) {
