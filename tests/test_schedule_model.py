@@ -71,3 +71,38 @@ def test_model_rejects_unsafe_variants(skew, lead):
     if lead:     # with the neighbour E, pixel 0 is read three steps after it was written: a ring of 4 is then too short
         assert any(h[0] == "overwritten-before-read" for h in simulate(skew, lead, sync2=True, ring=4))
     assert any(h[0] == "overwritten-before-read" for h in simulate(skew, lead, sync2=False, ring=1))
+
+
+def simulate_chunked(skew, use_e, ring=4, n_i=40, warps=16):
+    """The experimental chunk-skipping kernel (agg_chunked.cuh): one scanline per warp, a barrier after every step,
+    warp k at pixel t - k*skew; it reads pixels i-1, i (and i+1 with the neighbour E) of the previous warp's ring and
+    pixel i-1 of its own."""
+    written, reads = {}, {}
+    for t in range(n_i + (warps - 1) * skew):
+        for k in range(warps):
+            i = t - k * skew
+            if not 0 <= i < n_i:
+                continue
+            written[(k, i)] = t
+            if 0 < i < n_i - 1:                      # border pixels read nothing
+                reads[(k, i - 1)] = max(reads.get((k, i - 1), -1), t)            # own previous pixel
+                if k >= 1:
+                    for j in (i - 1, i) + ((i + 1,) if use_e else ()):
+                        reads[(k - 1, j)] = max(reads.get((k - 1, j), -1), t)
+    hazards = []
+    for (k, j), r in reads.items():
+        w = written.get((k, j))
+        if w is None or not w < r:
+            hazards.append(("read-before-write", k, j, w, r))
+        over = written.get((k, j + ring))
+        if over is not None and not r < over:
+            hazards.append(("overwritten-before-read", k, j, r, over))
+    return hazards
+
+
+@pytest.mark.parametrize("skew,use_e", [(1, False), (2, True)])
+def test_chunked_kernel_schedule(skew, use_e):
+    assert simulate_chunked(skew, use_e, ring=4) == []
+    assert simulate_chunked(skew, use_e, ring=2) != []          # the model has teeth
+    if use_e:
+        assert simulate_chunked(1, True) != []                  # E needs the two-pixel skew
