@@ -561,6 +561,81 @@ __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 64)
     }
 }
 
+// EXPERIMENTAL companion of agg_chunked.cuh (S2PB_CHUNKED=1, not yet run on a GPU): the same WTA for slabs whose
+// pixels use few of their 32-label chunks.  A warp owns a pixel and only reads the chunks [ea, eb] that hold its
+// label range (slot 32*e + lane), so a 40-label pixel of a 512-slot slab reads 2 x 128 B per pass instead of 2 KB.
+// Per lane it keeps, for every pass, the running minimum and the LAST slot attaining it, and for S the running
+// first minimum; S itself goes to shared memory for the sub-pixel fit.  Same arithmetic as wta_kernel.
+__global__ void __launch_bounds__(kWtaThreads) wta_chunked_kernel(const WtaParams P, int DP)
+{
+    extern __shared__ float sS_all[];                    // [warps][DP]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *sS = sS_all + (size_t)wib * DP;
+    const __half *C = reinterpret_cast<const __half *>(P.C);
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < P.npix; p += nwarps) {
+        const int lo = P.lo[p] - P.gmin, hi = P.hi[p] - P.gmin;      // slots
+        const int ea = lo >> 5, eb = hi >> 5;
+        float pm[kMaxPasses];
+        int pa[kMaxPasses];
+#pragma unroll
+        for (int d = 0; d < kMaxPasses; d++) { pm[d] = S2PB_INF; pa[d] = -1; }
+        float best = S2PB_INF;
+        int bidx = 0x7fffffff;
+        for (int e = ea; e <= eb; e++) {
+            const int kk = 32 * e + lane;
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < kMaxPasses; d++)
+                if (d < P.ndir) {
+                    const float v = __ldcg(P.L[d] + p * DP + kk);
+                    if (v < pm[d]) { pm[d] = v; pa[d] = kk; } else if (v == pm[d]) pa[d] = kk;
+                    s += v;
+                }
+            const float c = cost_value(__half_as_ushort(C[p * DP + kk]), P.lut);
+            if (P.fix_overcount == 1) s = fmaf(-(float)(P.ndir - 1), c, s);
+            if (isfinite(s) && best > s) { best = s; bidx = kk; }
+            sS[kk] = s;
+        }
+        // per pass: the LAST slot of the whole vector attaining its minimum (mgm_core.cc:1015-1019)
+        int confi_src[kMaxPasses];
+#pragma unroll
+        for (int d = 0; d < kMaxPasses; d++) {
+            confi_src[d] = -1;
+            if (d < P.ndir) {
+                const float md = warp_min_f32(pm[d]);
+                confi_src[d] = __reduce_max_sync(0xffffffffu, (pm[d] == md) ? pa[d] : -1);
+            }
+        }
+        const float m = warp_min_f32(best);
+        int kbest = __reduce_min_sync(0xffffffffu, (best == m && bidx != 0x7fffffff) ? bidx : 0x7fffffff);
+        if (kbest > DP - 1) kbest = 0;
+        const int o = P.gmin + kbest;
+        float minP = (float)o, minL = m;
+        int confi = 0;
+#pragma unroll
+        for (int d = 0; d < kMaxPasses; d++) confi += (confi_src[d] == kbest) ? 1 : 0;
+        __syncwarp();
+        if (P.refine != 0 && lane == 0) {
+            if (kbest - 1 >= lo && kbest + 2 <= hi) {                 // o - 1 >= lo_label && o + 2 <= hi_label
+                const float v0 = sS[kbest - 1], v1 = sS[kbest], v2 = sS[kbest + 1];
+                float dx = 0.f, dxr = 0.f, ml = minL, mlr = minP;
+                if (P.refine == 1) { vfit3(v0, v1, v2, ml, dx); vfit3(v2, v1, v0, mlr, dxr); }
+                else { parabola3(v0, v1, v2, ml, dx); parabola3(v2, v1, v0, mlr, dxr); }
+                minP = (float)o + dx;
+                minL = ml;
+                if (mlr < ml) { minP = (float)o - dxr; minL = mlr; }
+            }
+        }
+        if (lane == 0) {
+            P.disp[p] = __fdiv_rn(minP, P.inv_zoom_div);
+            if (P.cost) P.cost[p] = minL;
+            if (P.conf) P.conf[p] = (float)confi;
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ image-space post filters
 
 // median_filter, img_tools.h:204-238: window clipped to the image, NaN skipped, element

@@ -485,8 +485,18 @@ static int launch_cost_gen(s2pb_ctx *ctx, int LPL, const CostGenParams &P, cudaS
     ctx->launches++;
     return S2PB_OK;
 }
-static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t st, bool general = false)
+static bool chunked_enabled();
+static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t st, bool general = false, bool ragged = false)
 {
+    if (ragged && !general && P.S == nullptr && chunked_enabled()) {      // experimental, mgm_multi levels only
+        const int DP = 32 * LPL;
+        static bool configured = false;
+        if (!configured) { CK(cudaFuncSetAttribute(wta_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 512 * 4)); configured = true; }
+        wta_chunked_kernel<<<ctx->sm_count * 16, kWtaThreads, (size_t)(kWtaThreads / 32) * DP * sizeof(float), st>>>(P, DP);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        return S2PB_OK;
+    }
     LPL_SWITCH(LPL, launch_wta_t<K>(P, ctx->sm_count, st, general));
     CK(cudaGetLastError());
     ctx->launches++;
@@ -663,7 +673,7 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
         WtaParams W;
         fill_wta(W, s.v[vi], p->ndir, gminv[vi], p, lut, npix);
         W.inv_zoom_div = (float)zoom;
-        rc = launch_wta(ctx, LPL, W, st, general);
+        rc = launch_wta(ctx, LPL, W, st, general, true);
         if (rc != S2PB_OK) return rc;
     }
     TRACE(st, "  wta");
