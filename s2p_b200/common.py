@@ -10,7 +10,7 @@ import subprocess
 
 import numpy as np
 
-from . import _lib, rasterio_compat as rio
+from . import rasterio_compat as rio
 from .engine import S2pbError, get_engine
 
 

@@ -7,8 +7,6 @@ geo-referencing metadata is kept exactly as the reference keeps it.
 """
 import shutil
 
-import numpy as np
-
 from . import rasterio_compat as rio
 from .engine import get_engine
 

@@ -1,6 +1,6 @@
 """ncu raw CSV of scripts/all_kernels_probe.py -> per-kernel table (time, DRAM bytes, GB/s, fraction of the measured peak).
 usage: ncu -i rep --page raw --csv | python scripts/kernel_table.py [peak_GBps] > profiles/xxx.md"""
-import csv, sys, json, os
+import csv, sys
 peak = float(sys.argv[1]) if len(sys.argv) > 1 else 6567.7
 rows = list(csv.reader(sys.stdin))
 hdr, units = rows[0], rows[1]

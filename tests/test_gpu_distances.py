@@ -150,7 +150,6 @@ def test_mgm_multi_distance(engine, oracle):
 def test_against_reference_golden_vectors(engine, name):
     """tests/golden/*.npz are outputs of the unmodified reference binary (tests/golden/make_golden.py)."""
     import make_golden as G
-    from s2p_b200 import _lib
     from s2p_b200.engine import default_params
     ref, sec, dmin, dmax, kw = G.inputs(name)
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
