@@ -4,7 +4,7 @@
 
 namespace s2pb {
 
-static constexpr int kCkMaxSmem = 227 * 1024;
+static constexpr int kCkMaxSmem = 224 * 1024;      // dynamic part: the 227 KB opt-in limit minus the static shared memory of the kernel
 
 int agg_chunked_configure()
 {
