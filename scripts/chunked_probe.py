@@ -15,7 +15,7 @@ from s2p_b200.synth import make_pair
 eng = Engine(0)
 cases = [((120, 160), -20, 20, 1, dict(subpix=1, remove_small_cc=0)), ((120, 160), -20, 20, 1, dict()), ((230, 260), -40, 40, 3, dict(scales=3))]
 if os.environ.get("BIG"):
-    cases.append(((532, 768), -128, 127, 5, dict()))
+    cases = [((532, 768), -128, 127, 5, dict())] if os.environ.get("BIG") == "only" else cases + [((532, 768), -128, 127, 5, dict())]
 eq = lambda a, b: int((~((a == b) | (np.isnan(a) & np.isnan(b)))).sum())
 for (h, w), dmin, dmax, seed, kw in cases:
     ref, sec, _ = make_pair(h, w, dmin, dmax, seed=seed)
@@ -26,6 +26,17 @@ for (h, w), dmin, dmax, seed, kw in cases:
     except Exception as e:
         print("case", (h, w), kw, "FAILED:", e, flush=True)
         break
-    d, c, dr = O.port.mgm_multi(ref, sec, dmin, dmax, O.mgm_multi_params(**kw))
+    ref_file = os.environ.get("COMPARE")       # compare with (or save for) another run instead of running the CPU oracle
+    if ref_file:
+        tag = "%s_%dx%d_%d.npz" % (ref_file, w, h, len(kw))
+        if os.path.exists(tag):
+            z = np.load(tag)
+            d, c, dr = z["d"], z["c"], z["dr"]
+        else:
+            np.savez(tag, d=out["disp"], c=out["conf"], dr=out["disp_right"])
+            print("case", (h, w), kw, "saved, %.1f ms" % (dt * 1e3), flush=True)
+            continue
+    else:
+        d, c, dr = O.port.mgm_multi(ref, sec, dmin, dmax, O.mgm_multi_params(**kw))
     print("case", (h, w), kw, "chunked" if os.environ.get("S2PB_CHUNKED") == "1" else "dense", "%.1f ms | mismatch disp %d conf %d dispR %d of %d" % (
         dt * 1e3, eq(out["disp"], d), eq(out["conf"], c), eq(out["disp_right"], dr), d.size), flush=True)
