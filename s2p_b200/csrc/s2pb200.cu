@@ -392,7 +392,10 @@ static void fill_pass(PassDesc &pd, int pass, int w, int h)
 // Enqueue the 8-pass aggregation of `nviews` views of slot s in ONE persistent launch.
 // S2PB_CHUNKED=1 in the environment routes the f16-cost aggregation of mgm_multi's levels to the experimental
 // chunk-skipping kernel (agg_chunked.cuh)
-static bool chunked_enabled() { static int v = -1; if (v < 0) { const char *e = getenv("S2PB_CHUNKED"); v = e ? atoi(e) != 0 : 0; } return v != 0; }
+// (1 = aggregation and WTA, 2 = aggregation only, 3 = WTA only: to isolate a difference)
+static int chunked_mode() { static int v = -1; if (v < 0) { const char *e = getenv("S2PB_CHUNKED"); v = e ? atoi(e) : 0; } return v; }
+static bool chunked_enabled() { return chunked_mode() == 1 || chunked_mode() == 2; }
+static bool chunked_wta_enabled() { return chunked_mode() == 1 || chunked_mode() == 3; }
 
 // general: the float-cost flavour; wgt[vi] = that view's weight image or nullptr (general only)
 // gminv: label of slot 0 per view (only needed by the chunk-skipping kernel; nullptr = dense kernel)
@@ -485,10 +488,10 @@ static int launch_cost_gen(s2pb_ctx *ctx, int LPL, const CostGenParams &P, cudaS
     ctx->launches++;
     return S2PB_OK;
 }
-static bool chunked_enabled();
+static bool chunked_wta_enabled();
 static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t st, bool general = false, bool ragged = false)
 {
-    if (ragged && !general && P.S == nullptr && chunked_enabled()) {      // experimental, mgm_multi levels only
+    if (ragged && !general && P.S == nullptr && chunked_wta_enabled()) {  // experimental, mgm_multi levels only
         const int DP = 32 * LPL;
         static bool configured = false;
         if (!configured) { CK(cudaFuncSetAttribute(wta_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 512 * 4)); configured = true; }
