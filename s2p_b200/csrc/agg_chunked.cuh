@@ -1,4 +1,4 @@
-// agg_chunked.cuh -- EXPERIMENTAL (off by default, S2PB_CHUNKED=1 selects it; not yet run on a GPU): the MGM
+// agg_chunked.cuh -- EXPERIMENTAL (off by default, S2PB_CHUNKED=1 selects it): the MGM
 // aggregation for volumes whose pixels use a small part of the slab, i.e. the fine levels of mgm_multi.
 //
 // Why.  update_dmin_dmax gives most pixels of a fine level 17..40 labels but hands the parent's full range to every
@@ -17,6 +17,11 @@
 //     kernels and the band hand-off through L2 work unchanged.
 // The label range of a pixel only enters through its span; slots of an active chunk outside the range hold +INF
 // costs and therefore +INF results, exactly as in the dense kernel.
+// Status: scripts/chunked_emulator.py replays this file's indexing on the CPU (ring slots, guards, staging slots,
+// range words, previous-band ring) and equals the oracle bit for bit for every TSGM and slab width; it found the
+// chunk-edge case of term() below (a neighbour whose span starts right after / ends right before my chunk), which
+// the first GPU run showed as 1.5 % differing pixels on the 512-slot level.  The corrected kernel has not run on a
+// GPU yet, and version 1 is not faster than the dense kernel.
 #pragma once
 #include "agg_kernel.cuh"
 
@@ -173,6 +178,8 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
     auto term = [&](const Nb &n, int e, int kk) {
         float a = S2PB_INF, b = S2PB_INF, c0 = S2PB_INF;
         if (e >= n.ea && e <= n.eb) { a = n.v[kk - 1]; c0 = n.v[kk]; b = n.v[kk + 1]; }      // the guards make the span edges +INF
+        else if (e == n.ea - 1) { if (lane == 31) b = n.v[kk + 1]; }     // my last slot's right neighbour is the first slot of its span
+        else if (e == n.eb + 1) { if (lane == 0) a = n.v[kk - 1]; }      // my first slot's left neighbour is the last slot of its span
         const float v1 = fminf(a, b) + P1;
         return fmin3f(c0, v1, n.m + P2) - n.m;
     };
