@@ -13,8 +13,9 @@
 //   * one scanline per warp (16 warps per CTA) and the neighbours' vectors live in SHARED memory, read with
 //     offsets -1 / 0 / +1 (no shuffles, no register windows); every stored vector carries its chunk span and an
 //     +INF guard on both sides of the span, chunks of a neighbour outside its span read as +INF;
-//   * the chunks a pixel does not compute are written as +INF to the global L volume, so the dense cost and WTA
-//     kernels and the band hand-off through L2 work unchanged.
+//   * the chunks a pixel does not compute are either written as +INF to the global L volume (fill_inf: the dense WTA
+//     kernel then works on the result) or left untouched (the chunk-skipping WTA of mgm_kernels.cuh never reads
+//     them; the band hand-off then carries the previous band's spans as well).
 // The label range of a pixel only enters through its span; slots of an active chunk outside the range hold +INF
 // costs and therefore +INF results, exactly as in the dense kernel.
 // Status: scripts/chunked_emulator.py replays this file's indexing on the CPU (ring slots, guards, staging slots,
@@ -39,12 +40,14 @@ struct ChunkedParams {
     const short *lo[kMaxPV], *hi[kMaxPV];   // per pass-view: the view's per-pixel label range
     int gmin[kMaxPV];                       // ... and the label of slot 0
     int DP;                                 // slots per pixel (multiple of 32, <= 512)
+    int fill_inf;                           // 1: write +INF to the chunks a pixel skips (the dense WTA kernel then works on the
+                                            // result); 0: leave them untouched (the chunk-skipping WTA never reads them)
 };
 
 // shared memory carve-up for a run-time DP
 struct CkSmem {
     int DP, vstride;                        // vstride = DP + 2 * kCkPad floats per stored vector
-    size_t ring_off, meta_off, r0_off, r0m_off, cst_off, rng_off, bytes;
+    size_t ring_off, meta_off, r0_off, r0m_off, cst_off, rng_off, r0rng_off, bytes;
     __host__ __device__ explicit CkSmem(int dp) : DP(dp), vstride(dp + 2 * kCkPad)
     {
         ring_off = 0;                                                               // float [warps][ring][vstride]
@@ -53,14 +56,15 @@ struct CkSmem {
         r0m_off = r0_off + sizeof(float) * kCkR0 * vstride;                         // float [kCkR0]
         cst_off = (r0m_off + sizeof(float) * kCkR0 + 15) / 16 * 16;                 // half [warps][stage][DP]
         rng_off = cst_off + sizeof(__half) * kCkWarps * kCkStage * dp;              // 2 words per (warp, stage): lo, hi
-        bytes = rng_off + 8 * kCkWarps * kCkStage;
+        r0rng_off = rng_off + 8 * kCkWarps * kCkStage;                              // 2 words per previous-band slot
+        bytes = r0rng_off + 8 * kCkR0;
     }
 };
 
 template <int TSGM, int TYPE, bool SCALED>
 __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short *__restrict__ lo_img, const short *__restrict__ hi_img,
-                                                 int gmin, int DP, int band, float P1, float P2, const float *__restrict__ lut,
-                                                 const int *abort_flag, unsigned char *smem)
+                                                 int gmin, int DP, bool fill_inf, int band, float P1, float P2,
+                                                 const float *__restrict__ lut, const int *abort_flag, unsigned char *smem)
 {
     constexpr bool useA = (TYPE == 0) ? true : (TSGM == 4);
     constexpr bool useCn = (TYPE == 0) ? (TSGM >= 2) : (TSGM >= 3);
@@ -91,6 +95,7 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
     float *r0m = reinterpret_cast<float *>(smem + SM.r0m_off);
     const __half *cst = reinterpret_cast<const __half *>(smem + SM.cst_off) + (size_t)k * kCkStage * DP;
     const unsigned *rng = reinterpret_cast<const unsigned *>(smem + SM.rng_off) + k * kCkStage * 2;
+    const unsigned *r0rng = reinterpret_cast<const unsigned *>(smem + SM.r0rng_off);
     float *myring = ring + (size_t)k * kCkRing * VS;
     float *mymeta = meta + k * kCkRing * 3;
     const float *srcring = from_r0 ? r0 : ring + (size_t)(k - 1) * kCkRing * VS;
@@ -118,7 +123,8 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
     const char *psrc = reinterpret_cast<const char *>(pd.L + prevbase * DP);
     const float *pmsrc = pd.Lmin + prevbase;
     const long long lstepb = strideI * (long long)(DP * 4);
-    const unsigned r0_s = smem_s + (unsigned)SM.r0_off, r0m_s = smem_s + (unsigned)SM.r0m_off;
+    const unsigned r0_s = smem_s + (unsigned)SM.r0_off, r0m_s = smem_s + (unsigned)SM.r0m_off, r0rng_s = smem_s + (unsigned)SM.r0rng_off;
+    long long ppix = prevbase;                               // pixel index of the previous-band pixel to stage next
     const int *prev_progress = (band > 0) ? pd.progress + (band - 1) : nullptr;
     int jp = 0, avail = 0;
 
@@ -145,8 +151,11 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
                 const unsigned slot = (unsigned)(jp & (kCkR0 - 1));
                 for (int c = lane; c < DP / 4; c += 32) cp_async16_s(r0_s + (slot * VS + kCkPad) * 4 + 16 * c, psrc + 16 * c);
                 if (lane == 0) cp_async4_s(r0m_s + slot * 4, pmsrc);
+                if (lane == 1) cp_async4_s(r0rng_s + slot * 8, reinterpret_cast<const char *>(lo_img) + ((ppix * 2) & ~3LL));
+                if (lane == 2) cp_async4_s(r0rng_s + slot * 8 + 4, reinterpret_cast<const char *>(hi_img) + ((ppix * 2) & ~3LL));
                 psrc += lstepb;
                 pmsrc += strideI;
+                ppix += strideI;
             }
             jp++;
         }
@@ -164,10 +173,17 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
             const int slot = j & (kCkRing - 1);
             n.v = myring + slot * VS + kCkPad;
             n.m = mymeta[slot * 3]; n.ea = __float_as_int(mymeta[slot * 3 + 1]); n.eb = __float_as_int(mymeta[slot * 3 + 2]);
-        } else if (from_r0) {           // previous band: the global vector is complete (+INF outside the span)
+        } else if (from_r0) {           // previous band: the whole vector was copied, only its span is meaningful
             const int slot = j & srcmask;
-            n.v = r0 + slot * VS + kCkPad;
-            n.m = r0m[slot]; n.ea = 0; n.eb = NC - 1;
+            float *v = r0 + slot * VS + kCkPad;
+            const long long qpix = prevbase + (long long)j * strideI;
+            const int sh = (int)((qpix & 1) * 16);
+            const int qlo = (int)(short)((r0rng[slot * 2] >> sh) & 0xffff), qhi = (int)(short)((r0rng[slot * 2 + 1] >> sh) & 0xffff);
+            n.ea = (qlo - gmin) >> 5; n.eb = (qhi - gmin) >> 5;
+            if (lane == 0) { v[32 * n.ea - 1] = S2PB_INF; v[32 * (n.eb + 1)] = S2PB_INF; }     // guards (the copy brought whatever the chunks next to the span hold)
+            __syncwarp();
+            n.v = v;
+            n.m = r0m[slot];
         } else {
             const int slot = j & srcmask;
             n.v = srcring + slot * VS + kCkPad;
@@ -241,7 +257,7 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
                     mine[kk] = L;
                     lm = fminf(lm, L);
                 }
-                out[kk] = L;                                   // +INF for the chunks outside my span
+                if (fill_inf || (e >= ea && e <= eb)) out[kk] = L;          // +INF for the chunks outside my span, if asked for
             }
             const float m = warp_min_f32(lm);
             if (lane == 0) {
@@ -282,8 +298,8 @@ __global__ void __launch_bounds__(kCkThreads) aggregate_chunked_kernel(const __g
         const int band = item / P.A.nPV, pvi = item - band * P.A.nPV;
         const PassDesc &pd = P.A.pv[pvi];
         if (band >= (pd.nS + kCkWarps - 1) / kCkWarps) continue;
-        if (pd.type == 0) run_band_chunked<TSGM, 0, SCALED>(pd, P.lo[pvi], P.hi[pvi], P.gmin[pvi], P.DP, band, P.A.P1, P.A.P2, P.A.lut, P.A.abort_flag, smem);
-        else run_band_chunked<TSGM, 1, SCALED>(pd, P.lo[pvi], P.hi[pvi], P.gmin[pvi], P.DP, band, P.A.P1, P.A.P2, P.A.lut, P.A.abort_flag, smem);
+        if (pd.type == 0) run_band_chunked<TSGM, 0, SCALED>(pd, P.lo[pvi], P.hi[pvi], P.gmin[pvi], P.DP, P.fill_inf != 0, band, P.A.P1, P.A.P2, P.A.lut, P.A.abort_flag, smem);
+        else run_band_chunked<TSGM, 1, SCALED>(pd, P.lo[pvi], P.hi[pvi], P.gmin[pvi], P.DP, P.fill_inf != 0, band, P.A.P1, P.A.P2, P.A.lut, P.A.abort_flag, smem);
     }
 }
 

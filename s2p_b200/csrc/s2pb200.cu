@@ -426,6 +426,7 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
         memset(&Q, 0, sizeof Q);
         Q.A = P;
         Q.DP = 32 * LPL;
+        Q.fill_inf = chunked_wta_enabled() ? 0 : 1;          // the dense WTA reads every chunk
         int q = 0;
         for (int vi = 0; vi < nviews; vi++)
             for (int p = 0; p < ndir; p++, q++) { Q.lo[q] = s.v[vi].lo; Q.hi[q] = s.v[vi].hi; Q.gmin[q] = gminv[vi]; }

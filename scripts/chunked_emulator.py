@@ -15,6 +15,7 @@ F = np.float32
 INF = F(np.inf)
 W_, RING, STAGE, R0, PAD, PUBLISH = 16, 4, 4, 8, 4, 8
 FIXED = os.environ.get("EMU_BUGGY") != "1"      # EMU_BUGGY=1 reproduces the first version of the kernel (chunk-edge bug)
+FILL_INF = os.environ.get("EMU_FILL_INF") == "1"   # 1: the variant that writes +INF to the skipped chunks of the global volume
 
 
 def fill_pass(p, w, h):
@@ -49,6 +50,7 @@ def run_pass(pd, C, lo_img, hi_img, gmin, DP, tsgm, P1, P2, L, Lmin):
         r0[:, PAD + DP:] = INF
         cst = np.full((W_, STAGE, DP), F(333.0), F)
         rng = np.zeros((W_, STAGE, 2), np.uint32)
+        r0rng = np.zeros((R0, 2), np.uint32)
         st = []
         for k in range(W_):
             s = band * W_ + k
@@ -75,6 +77,8 @@ def run_pass(pd, C, lo_img, hi_img, gmin, DP, tsgm, P1, P2, L, Lmin):
                     q = w["prevbase"] + w["jp"] * sI
                     r0[slot, PAD:PAD + DP] = L[q]
                     r0m[slot] = Lmin[q]
+                    r0rng[slot, 0] = lo_words[(q * 2 & ~3) // 4]
+                    r0rng[slot, 1] = hi_words[(q * 2 & ~3) // 4]
                 w["jp"] += 1
 
         def nb_at(k, j, mine):
@@ -83,7 +87,15 @@ def run_pass(pd, C, lo_img, hi_img, gmin, DP, tsgm, P1, P2, L, Lmin):
                 return ring[k, slot], F(meta[k, slot, 0]), int(meta[k, slot, 1]), int(meta[k, slot, 2])
             if k == 0:
                 slot = j & (R0 - 1)
-                return r0[slot], r0m[slot], 0, NC - 1
+                qpix = st[0]["prevbase"] + j * sI
+                sh = (qpix & 1) * 16
+                s16 = lambda v: v - 65536 if v >= 32768 else v
+                qlo, qhi = s16((int(r0rng[slot, 0]) >> sh) & 0xffff), s16((int(r0rng[slot, 1]) >> sh) & 0xffff)
+                assert qlo == lo_img[qpix] and qhi == hi_img[qpix], "previous-band range word mismatch"
+                ea, eb = (qlo - gmin) >> 5, (qhi - gmin) >> 5
+                r0[slot, PAD + 32 * ea - 1] = INF
+                r0[slot, PAD + 32 * (eb + 1)] = INF
+                return r0[slot], r0m[slot], ea, eb
             slot = j & (RING - 1)
             return ring[k - 1, slot], F(meta[k - 1, slot, 0]), int(meta[k - 1, slot, 1]), int(meta[k - 1, slot, 2])
 
@@ -130,7 +142,7 @@ def run_pass(pd, C, lo_img, hi_img, gmin, DP, tsgm, P1, P2, L, Lmin):
                     nE = nb_at(k, i + 1, False) if useE else None
                 mine = ring[k, i & (RING - 1)]
                 lm = np.full(32, INF, F)
-                outv = np.full(DP, INF, F)
+                outv = np.full(DP, INF, F) if FILL_INF else L[w["outpix"]].copy()
                 for e in range(NC):
                     kk = 32 * e + lane
                     if ea <= e <= eb:
@@ -218,7 +230,10 @@ def main():
     ea, eb = (lo.reshape(-1) - gmin) >> 5, (hi.reshape(-1) - gmin) >> 5
     e_of = (np.arange(DP) >> 5)[None, :]
     outside = (e_of < ea[:, None]) | (e_of > eb[:, None])
-    print("skipped chunks all +INF:", bool(np.all(np.isinf(Ls[0][outside]))))
+    if FILL_INF:
+        print("skipped chunks all +INF:", bool(np.all(np.isinf(Ls[0][outside]))))
+    else:
+        print("skipped chunks untouched:", bool(np.all(Ls[0][outside] == np.float32(-1.0))))
 
 
 if __name__ == "__main__":

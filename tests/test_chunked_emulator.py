@@ -20,8 +20,11 @@ def _run(args, env=None):
 
 @pytest.mark.parametrize("dp,h,w,tsgm", [(64, 20, 24, 3), (96, 18, 35, 4), (512, 17, 20, 2), (64, 33, 9, 1)])
 def test_emulated_kernel_equals_oracle(dp, h, w, tsgm):
-    out = _run([dp, h, w, tsgm, 3])
-    assert ": 0 of " in out and "skipped chunks all +INF: True" in out, out
+    out = _run([dp, h, w, tsgm, 3])                              # skipped chunks are left untouched (chunk-skipping WTA)
+    assert ": 0 of " in out and "skipped chunks untouched: True" in out, out
+    if dp <= 96:
+        out = _run([dp, h, w, tsgm, 3], env={"EMU_FILL_INF": "1"})   # ... or written as +INF (dense WTA)
+        assert ": 0 of " in out and "skipped chunks all +INF: True" in out, out
 
 
 def test_emulator_catches_the_chunk_edge_bug():
