@@ -118,6 +118,18 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
     const unsigned rdst = smem_s + (unsigned)SM.rng_off + (unsigned)(k * kCkStage * 8);
     long long pidx = rowbase;                                // pixel index of the pixel to stage next
     int jc = 0;
+    // chunk span of the pixels about to be staged: their range words are fetched with plain (L2-resident, warp-uniform)
+    // loads two stagings ahead and wait in registers, so that only the chunks of the span are copied
+    auto range_words = [&](int j, unsigned &wl, unsigned &wh) {
+        wl = wh = 0;
+        if (live && j < nI) {
+            const long long q = rowbase + (long long)j * strideI;
+            wl = __ldg(reinterpret_cast<const unsigned *>(reinterpret_cast<const char *>(lo_img) + ((q * 2) & ~3LL)));
+            wh = __ldg(reinterpret_cast<const unsigned *>(reinterpret_cast<const char *>(hi_img) + ((q * 2) & ~3LL)));
+        }
+    };
+    unsigned nl0, nh0, nl1, nh1, nl2, nh2;                    // words of pixels jc, jc + 1, jc + 2
+    range_words(0, nl0, nh0); range_words(1, nl1, nh1); range_words(2, nl2, nh2);
     const bool stage_prev = prev && from_r0;
     const long long prevbase = rowbase - pd.strideS;
     const char *psrc = reinterpret_cast<const char *>(pd.L + prevbase * DP);
@@ -131,7 +143,10 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
     auto stage_mine = [&]() {
         if (live && jc < nI) {
             const unsigned slot = (unsigned)(jc & (kCkStage - 1));
-            for (int c = lane; c < DP / 8; c += 32) cp_async16_s(cdst + slot * (unsigned)(DP * 2) + 16 * c, csrc + 16 * c);
+            const int sh = (int)((pidx & 1) * 16);
+            const int ea = ((int)(short)((nl0 >> sh) & 0xffff) - gmin) >> 5, eb = ((int)(short)((nh0 >> sh) & 0xffff) - gmin) >> 5;
+            for (int c = 4 * ea + lane; c <= 4 * eb + 3; c += 32)            // a chunk of 32 halfs = four 16-byte pieces
+                cp_async16_s(cdst + slot * (unsigned)(DP * 2) + 16 * c, csrc + 16 * c);
             // the 4-byte words that hold lo[pidx] and hi[pidx] (2-byte elements): the half is picked at use time
             if (lane == 0) cp_async4_s(rdst + slot * 8, reinterpret_cast<const char *>(lo_img) + ((pidx * 2) & ~3LL));
             if (lane == 1) cp_async4_s(rdst + slot * 8 + 4, reinterpret_cast<const char *>(hi_img) + ((pidx * 2) & ~3LL));
@@ -139,6 +154,8 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
             pidx += strideI;
         }
         jc++;
+        nl0 = nl1; nh0 = nh1; nl1 = nl2; nh1 = nh2;
+        range_words(jc + 2, nl2, nh2);
     };
     auto stage_prevband = [&]() {
         if (stage_prev) {

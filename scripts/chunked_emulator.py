@@ -59,15 +59,29 @@ def run_pass(pd, C, lo_img, hi_img, gmin, DP, tsgm, P1, P2, L, Lmin):
             st.append(dict(s=s, live=live, rowbase=rowbase, prev=usePrev and live and s > 0, jc=0, pidx=rowbase, jp=0, upix=rowbase,
                            outpix=rowbase, prevbase=rowbase - sS))
 
+        def range_words(k, j):
+            w = st[k]
+            if w["live"] and j < nI:
+                q = w["rowbase"] + j * sI
+                return int(lo_words[(q * 2 & ~3) // 4]), int(hi_words[(q * 2 & ~3) // 4])
+            return 0, 0
+        for k in range(W_):
+            st[k]["nw"] = [range_words(k, 0), range_words(k, 1), range_words(k, 2)]
+
         def stage_mine(k):
             w = st[k]
             if w["live"] and w["jc"] < nI:
                 slot = w["jc"] & (STAGE - 1)
-                cst[k, slot] = C[w["pidx"]]
+                sh = (w["pidx"] & 1) * 16
+                s16 = lambda v: v - 65536 if v >= 32768 else v
+                ea = (s16((w["nw"][0][0] >> sh) & 0xffff) - gmin) >> 5
+                eb = (s16((w["nw"][0][1] >> sh) & 0xffff) - gmin) >> 5
+                cst[k, slot, 32 * ea:32 * (eb + 1)] = C[w["pidx"], 32 * ea:32 * (eb + 1)]      # only the chunks of the span
                 rng[k, slot, 0] = lo_words[(w["pidx"] * 2 & ~3) // 4]
                 rng[k, slot, 1] = hi_words[(w["pidx"] * 2 & ~3) // 4]
                 w["pidx"] += sI
             w["jc"] += 1
+            w["nw"] = [w["nw"][1], w["nw"][2], range_words(k, w["jc"] + 2)]
 
         def stage_prevband(k):
             w = st[k]
