@@ -394,8 +394,11 @@ static void fill_pass(PassDesc &pd, int pass, int w, int h)
 // chunk-skipping kernel (agg_chunked.cuh)
 // (1 = aggregation and WTA, 2 = aggregation only, 3 = WTA only: to isolate a difference)
 static int chunked_mode() { static int v = -1; if (v < 0) { const char *e = getenv("S2PB_CHUNKED"); v = e ? atoi(e) : 0; } return v; }
-static bool chunked_enabled() { return chunked_mode() == 1 || chunked_mode() == 2; }
-static bool chunked_wta_enabled() { return chunked_mode() == 1 || chunked_mode() == 3; }
+// slabs narrower than S2PB_CHUNKED_MIN_DP slots (default 160) stay with the dense kernels: on the coarse levels most
+// pixels use most of their chunks (scripts/range_width_analysis.py)
+static int chunked_min_dp() { static int v = -1; if (v < 0) { const char *e = getenv("S2PB_CHUNKED_MIN_DP"); v = e ? atoi(e) : 160; } return v; }
+static bool chunked_enabled(int DP) { return (chunked_mode() == 1 || chunked_mode() == 2) && DP >= chunked_min_dp(); }
+static bool chunked_wta_enabled(int DP) { return (chunked_mode() == 1 || chunked_mode() == 3) && DP >= chunked_min_dp(); }
 
 // general: the float-cost flavour; wgt[vi] = that view's weight image or nullptr (general only)
 // gminv: label of slot 0 per view (only needed by the chunk-skipping kernel; nullptr = dense kernel)
@@ -421,12 +424,12 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
     P.P1 = P1; P.P2 = P2; P.next_item = s.next_item; P.abort_flag = ctx->abort_flag; P.lut = general ? nullptr : lut;
     P.general = general ? 1 : 0;
     CK(cudaMemsetAsync(s.next_item, 0, 4, st));
-    if (!general && gminv && chunked_enabled()) {
+    if (!general && gminv && chunked_enabled(32 * LPL)) {
         ChunkedParams Q;
         memset(&Q, 0, sizeof Q);
         Q.A = P;
         Q.DP = 32 * LPL;
-        Q.fill_inf = chunked_wta_enabled() ? 0 : 1;          // the dense WTA reads every chunk
+        Q.fill_inf = chunked_wta_enabled(32 * LPL) ? 0 : 1;   // the dense WTA reads every chunk
         int q = 0;
         for (int vi = 0; vi < nviews; vi++)
             for (int p = 0; p < ndir; p++, q++) { Q.lo[q] = s.v[vi].lo; Q.hi[q] = s.v[vi].hi; Q.gmin[q] = gminv[vi]; }
@@ -489,10 +492,10 @@ static int launch_cost_gen(s2pb_ctx *ctx, int LPL, const CostGenParams &P, cudaS
     ctx->launches++;
     return S2PB_OK;
 }
-static bool chunked_wta_enabled();
+static bool chunked_wta_enabled(int DP);
 static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t st, bool general = false, bool ragged = false)
 {
-    if (ragged && !general && P.S == nullptr && chunked_wta_enabled()) {  // experimental, mgm_multi levels only
+    if (ragged && !general && P.S == nullptr && chunked_wta_enabled(32 * LPL)) {  // experimental, mgm_multi levels only
         const int DP = 32 * LPL;
         static bool configured = false;
         if (!configured) { CK(cudaFuncSetAttribute(wta_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 512 * 4)); configured = true; }

@@ -1,6 +1,7 @@
 """First contact of the experimental chunk-skipping aggregation (S2PB_CHUNKED=1) with a GPU: mgm_multi on small
 tiles against the oracle, with a matcher timeout so that a deadlock is drained through the abort flag.
-usage: S2PB_CHUNKED=1 python scripts/chunked_probe.py   (and once with S2PB_CHUNKED=0 for the timing of the dense kernel)"""
+usage: S2PB_CHUNKED=1 S2PB_CHUNKED_MIN_DP=0 python scripts/chunked_probe.py   (MIN_DP=0: also on the narrow slabs of the small
+cases; once with S2PB_CHUNKED=0 for the timing of the dense kernels; BIG=only COMPARE=/tmp/x for the 768x532x256 tile, dense first)"""
 import os
 import sys
 import time
