@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--cpu-procs", type=int, default=0, help="concurrent reference processes (0 = calibrate: all host cores, 1/2, 1/4)")
     ap.add_argument("--cpu-rows", type=int, default=32, help="rows of the CPU sample strips")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nan-border", type=float, default=0.0,
+                    help="fraction of the tile width turned into no-data strips (0 = the BASELINE workload; > 0 exercises the "
+                         "no-data sentinel range, which can widen the right view's slab: DESIGN.md, limits)")
     return ap.parse_args()
 
 
@@ -58,6 +61,7 @@ def config(a, world):
                         a.dmax - a.dmin + 1, a.tiles),
         "tile": [a.size, a.size], "dmin": a.dmin, "dmax": a.dmax, "labels": a.dmax - a.dmin + 1,
         "tiles_per_gpu_per_step": a.tiles, "tiles_in_flight": a.slots, "parallelism": "tile-shard x%d" % world,
+        "nan_border": a.nan_border,
         "l2": "per-tile working set %.1f GiB (8 float path volumes per view) >> 126 MB L2; inputs differ per tile" % (
             2 * 8 * 4.0 * a.size * a.size * (32 * ((a.dmax - a.dmin + 32) // 32)) / 2 ** 30 * 1.0625),
     }
@@ -206,7 +210,7 @@ def run_ours(a, rank, world, local_rank):
     eng.reserve(nslots, W, H, D)
 
     # synthetic rectified pairs, distinct per tile and per rank (seed = global tile id)
-    pairs = [make_pair(H, W, a.dmin, a.dmax, seed=rank * B + t)[:2] for t in range(B)]
+    pairs = [make_pair(H, W, a.dmin, a.dmax, seed=rank * B + t, nan_border=a.nan_border)[:2] for t in range(B)]
     d_ref = [torch.from_numpy(r).to(dev) for r, _ in pairs]
     d_sec = [torch.from_numpy(s).to(dev) for _, s in pairs]
     d_disp = [torch.empty((H, W), dtype=torch.float32, device=dev) for _ in range(B)]
@@ -233,7 +237,7 @@ def run_ours(a, rank, world, local_rank):
         for t in range(B):
             sl = t % nslots
             eng.mgm_device(sl, d_ref[t].data_ptr(), d_sec[t].data_ptr(), W, H, a.dmin, a.dmax, p, d_disp[t].data_ptr(),
-                           d_conf[t].data_ptr(), d_mask[t].data_ptr(), 0, nodata_hint=0, stream=streams[sl].cuda_stream)
+                           d_conf[t].data_ptr(), d_mask[t].data_ptr(), 0, nodata_hint=(2 if a.nan_border > 0 else 0), stream=streams[sl].cuda_stream)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -312,7 +316,7 @@ def run_ours(a, rank, world, local_rank):
     for k in range(max(3, min(a.steps, 10))):
         t = k % B
         eng.mgm_device(0, d_ref[t].data_ptr(), d_sec[t].data_ptr(), W, H, a.dmin, a.dmax, p, d_disp[t].data_ptr(),
-                       d_conf[t].data_ptr(), d_mask[t].data_ptr(), 0, nodata_hint=0, stream=streams[0].cuda_stream)
+                       d_conf[t].data_ptr(), d_mask[t].data_ptr(), 0, nodata_hint=(2 if a.nan_border > 0 else 0), stream=streams[0].cuda_stream)
         streams[0].synchronize()
         tm = eng.last_timings(0)
         agg_ms.append(tm["aggregate"])
