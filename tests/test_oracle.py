@@ -30,7 +30,7 @@ def test_port_matches_golden(oracle, name):
     assert same(dr, g["dispR"])
 
 
-@pytest.mark.parametrize("name", ["plain", "wide", "nan_ref", "tsgm4_o4", "census3"])
+@pytest.mark.parametrize("name", ["plain", "wide", "nan_ref", "tsgm4_o4", "census3", "real"])
 def test_identity_shift_equals_dct_shift_without_nodata(oracle, name):
     """The reference pushes the matched image of each view through a DCT round trip even for a zero
     shift (mgm_costvolume.cc:23-60).  That is the identity except on exactly-zero pixels (NaN -> 0), whose
