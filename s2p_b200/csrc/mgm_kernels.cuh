@@ -286,6 +286,46 @@ __global__ void unpad_cost_kernel(const float *__restrict__ C, size_t npix, int 
     Cout[i] = C[p * DP + k];
 }
 
+// EXPERIMENTAL companion of agg_chunked.cuh (S2PB_CHUNKED=1): the census cost volume written only on the 32-slot
+// chunks [ea, eb] that hold a pixel's label range (slot 32*e + lane); the chunk-skipping aggregation and WTA never
+// read the others.  Same values as cost_kernel on those chunks, including +INF on the slots of an active chunk that
+// lie outside the range and the all-invalid -> 0 rule (mgm_costvolume.cc:166-171).
+template <bool ZOOM2>
+__global__ void cost_chunked_kernel(const uint64_t *__restrict__ cu, const uint64_t *__restrict__ cv, const uint64_t *__restrict__ cv1,
+                                    int w, int h, const short *__restrict__ lo, const short *__restrict__ hi, int gmin, int DP,
+                                    __half *__restrict__ C)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t npix = (size_t)w * h;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t p = warp; p < npix; p += nwarps) {
+        const int x = (int)(p % w);
+        const size_t row = p - x;
+        const uint64_t a = cu[p];
+        const int l = lo[p], hgh = hi[p];
+        const int ea = (l - gmin) >> 5, eb = (hgh - gmin) >> 5;
+        __half *dst = C + p * DP;
+        bool anyfinite = false;
+        for (int e = ea; e <= eb; e++) {
+            const int o = gmin + 32 * e + lane;
+            float v = S2PB_INF;
+            if (o >= l && o <= hgh) {
+                int q = x + o;
+                const uint64_t *codes = cv;
+                if (ZOOM2) { q = x + (o >> 1); if (o & 1) codes = cv1; }
+                if (q >= 0 && q < w) { v = (float)__popcll(a ^ codes[row + q]); anyfinite = true; }
+            }
+            dst[32 * e + lane] = __float2half_rn(v);
+        }
+        if (!__any_sync(0xffffffffu, anyfinite)) {
+            for (int e = ea; e <= eb; e++) {
+                const int o = gmin + 32 * e + lane;
+                if (o >= l && o <= hgh) dst[32 * e + lane] = __float2half_rn(0.f);
+            }
+        }
+    }
+}
+
 // float volume (stage-level API) -> f16 slab with +INF padding, and back
 __global__ void pack_cost_kernel(const float *__restrict__ Cin, size_t npix, int D, int DP, __half *__restrict__ C)
 {

@@ -666,6 +666,13 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
             G.w = w; G.h = h; G.gmin = gminv[vi]; G.cost = p->cost; G.win = p->census_win; G.zoom = zoom;
             G.C = (float *)s.v[vi].C;
             rc = launch_cost_gen(ctx, LPL, G, st);
+        } else if (chunked_mode() == 1 && chunked_enabled(32 * LPL)) {      // experimental: only the chunks of each pixel's span
+            if (zoom == 2) cost_chunked_kernel<true><<<ctx->sm_count * 8, 256, 0, st>>>(s.v[vi].census, s.v[1 - vi].census, cen_half[1 - vi], w, h,
+                                                                                  lo[vi], hi[vi], gminv[vi], 32 * LPL, (__half *)s.v[vi].C);
+            else cost_chunked_kernel<false><<<ctx->sm_count * 8, 256, 0, st>>>(s.v[vi].census, s.v[1 - vi].census, nullptr, w, h,
+                                                                               lo[vi], hi[vi], gminv[vi], 32 * LPL, (__half *)s.v[vi].C);
+            ctx->launches++;
+            rc = cudaGetLastError() == cudaSuccess ? S2PB_OK : fail(S2PB_ERR_CUDA, "cost_chunked_kernel launch failed");
         } else {
             rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census, w, h, lo[vi], hi[vi], gminv[vi], s.v[vi].C, st,
                              zoom == 2 ? cen_half[1 - vi] : nullptr, zoom);
