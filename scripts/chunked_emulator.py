@@ -248,6 +248,82 @@ def main():
         print("skipped chunks all +INF:", bool(np.all(np.isinf(Ls[0][outside]))))
     else:
         print("skipped chunks untouched:", bool(np.all(Ls[0][outside] == np.float32(-1.0))))
+    if os.environ.get("EMU_WTA", "1") == "1":
+        main_wta(DP, h, w, tsgm, seed, Ls, Cf, lo.reshape(-1), hi.reshape(-1), gmin)
+
+
+def vfit3(v0, v1, v2):
+    """vfit3 of mgm_kernels.cuh (refine.h:70-92 with the fused minimum value) -> (vmin, xmin), float32"""
+    if v1 > v0 and v1 > v2:
+        return v1, F(0)
+    slope = v2 - v1
+    if (v2 - v1) < (v0 - v1):
+        slope = v0 - v1
+    xmin = (v0 - v2) / (F(2) * slope)
+    vmin = F(np.float64(xmin - F(1)) * np.float64(slope) + np.float64(v2))       # fmaf
+    return vmin, xmin
+
+
+def wta_chunked(Ls, Cf, lo, hi, gmin, DP, ndir=8, refine=1):
+    """wta_chunked_kernel of mgm_kernels.cuh, lane by lane: only the chunks of a pixel's span are read."""
+    npix = Cf.shape[0]
+    disp, conf = np.zeros(npix, F), np.zeros(npix, F)
+    lane = np.arange(32)
+    for p in range(npix):
+        slo, shi = int(lo[p]) - gmin, int(hi[p]) - gmin
+        ea, eb = slo >> 5, shi >> 5
+        pm = np.full((ndir, 32), INF, F)
+        pa = np.full((ndir, 32), -1, np.int64)
+        best, bidx = np.full(32, INF, F), np.full(32, 0x7fffffff, np.int64)
+        sS = np.full(DP, F(12345.0), F)
+        for e in range(ea, eb + 1):
+            kk = 32 * e + lane
+            s = np.zeros(32, F)
+            for d in range(ndir):
+                v = Ls[d][p, kk]
+                lt, eq = v < pm[d], v == pm[d]
+                pa[d] = np.where(lt | eq, kk, pa[d])
+                pm[d] = np.where(lt, v, pm[d])
+                s = s + v
+            with np.errstate(invalid="ignore"):
+                s = (np.float64(-(ndir - 1)) * Cf[p, kk].astype(np.float64) + s.astype(np.float64)).astype(F)
+            take = np.isfinite(s) & (best > s)
+            best, bidx = np.where(take, s, best), np.where(take, kk, bidx)
+            sS[kk] = s
+        am = []
+        for d in range(ndir):
+            md = pm[d].min()
+            am.append(int(np.where(pm[d] == md, pa[d], -1).max()))
+        m = best.min()
+        kbest = int(np.where((best == m) & (bidx != 0x7fffffff), bidx, 0x7fffffff).min())
+        if kbest > DP - 1:
+            kbest = 0
+        o = gmin + kbest
+        minP = F(o)
+        conf[p] = sum(1 for d in range(ndir) if am[d] == kbest)
+        if refine and kbest - 1 >= slo and kbest + 2 <= shi:
+            v0, v1, v2 = sS[kbest - 1], sS[kbest], sS[kbest + 1]
+            ml, dx = vfit3(v0, v1, v2)
+            mlr, dxr = vfit3(v2, v1, v0)
+            minP = F(o) + dx
+            if mlr < ml:
+                minP = F(o) - dxr
+        disp[p] = minP
+    return disp, conf
+
+
+def main_wta(DP, h, w, tsgm, seed, Ls, Cf, lo, hi, gmin):
+    """compare the emulated chunk-skipping WTA (on the emulated pass volumes, garbage outside the spans) with the oracle"""
+    import ctypes
+    npix = h * w
+    C3 = Cf.reshape(h, w, DP)
+    So, do, co, fo = O.port.aggregate(C3, lo.reshape(h, w), hi.reshape(h, w), gmin, 8.0, 32.0, 8, tsgm)
+    d_ref, c_ref = do.reshape(-1).copy(), co.reshape(-1).copy()
+    lo32, hi32 = np.ascontiguousarray(lo, np.int32), np.ascontiguousarray(hi, np.int32)
+    pf = lambda a, t=ctypes.c_float: a.ctypes.data_as(ctypes.POINTER(t))
+    O.lib().orc_refine(pf(np.ascontiguousarray(So)), pf(lo32, ctypes.c_int), pf(hi32, ctypes.c_int), npix, gmin, DP, 1, pf(d_ref), pf(c_ref))
+    d, cf = wta_chunked(Ls, Cf, lo, hi, gmin, DP)
+    print("chunk-skipping WTA: %d disparities and %d confidences of %d differ" % (int((d != d_ref).sum()), int((cf != fo.reshape(-1)).sum()), npix))
 
 
 if __name__ == "__main__":

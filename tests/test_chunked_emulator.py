@@ -22,6 +22,7 @@ def _run(args, env=None):
 def test_emulated_kernel_equals_oracle(dp, h, w, tsgm):
     out = _run([dp, h, w, tsgm, 3])                              # skipped chunks are left untouched (chunk-skipping WTA)
     assert ": 0 of " in out and "skipped chunks untouched: True" in out, out
+    assert "chunk-skipping WTA: 0 disparities and 0 confidences" in out, out
     if dp <= 96:
         out = _run([dp, h, w, tsgm, 3], env={"EMU_FILL_INF": "1"})   # ... or written as +INF (dense WTA)
         assert ": 0 of " in out and "skipped chunks all +INF: True" in out, out
