@@ -47,6 +47,9 @@ constexpr int kAggThreads = kNWC * 32;
 #ifndef S2PB_SYNC2
 #define S2PB_SYNC2 1
 #endif
+#ifndef S2PB_SPLIT_LOOP
+#define S2PB_SPLIT_LOOP 0
+#endif
 template <int LPL> struct SyncCfg {
     static constexpr bool sync2 = S2PB_SYNC2 && LPL > 4 && LPL <= 8;
     static constexpr int kRing = sync2 ? 8 : 4;      // ring slots per compute warp for handing vectors to the next warp
@@ -615,6 +618,31 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         else step(std::false_type{}, t, xB, xC, xE, hNew, hC, hE);
     };
 
+#if S2PB_SPLIT_LOOP
+    // EXPERIMENT (off by default, not yet measured): every warp runs its own three loops -- ramp-up, interior, ramp-down
+    // -- so that the interior steps carry no fast / slow test; the barrier sequence is the same for all warps.
+    auto group = [&](auto fast_c, const int t) {
+        if constexpr (U == 2) {
+            step(fast_c, t, x1, x0, x2, h0, h1, h2);
+            step(fast_c, t + 1, x0, x1, x2, h1, h0, h2);
+        } else {
+            step(fast_c, t, x1, x2, x0, h0, h1, h2);
+            step(fast_c, t + 1, x2, x0, x1, h1, h2, h0);
+            step(fast_c, t + 2, x0, x1, x2, h2, h0, h1);
+        }
+    };
+    int ta = nsteps, tb = nsteps;                          // [ta, tb): groups whose U steps are all interior for this warp
+    if (can_fast) {
+        ta = (fast_lo + U - 1) / U * U;
+        tb = (fast_hi + 1) / U * U;
+        if (tb < ta) tb = ta;
+        if (ta > nsteps) ta = tb = nsteps;
+    }
+    int t = 0;
+    for (; t < ta; t += U) group(std::false_type{}, t);
+    for (; t < tb; t += U) group(std::true_type{}, t);
+    for (; t < nsteps; t += U) group(std::false_type{}, t);
+#else
     for (int t = 0; t < nsteps; t += U) {
         if constexpr (U == 2) {
             do_step(t, x1, x0, x2, h0, h1, h2);
@@ -625,6 +653,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             do_step(t + 2, x0, x1, x2, h2, h0, h1);
         }
     }
+#endif
     cp_async_wait<0>();
 }
 
