@@ -54,7 +54,10 @@ template <int LPL> struct SyncCfg {
     static constexpr bool sync2 = S2PB_SYNC2 && LPL > 4 && LPL <= 8;
     static constexpr int kRing = sync2 ? 8 : 4;      // ring slots per compute warp for handing vectors to the next warp
 };
-constexpr int kPublish = 8;   // a band publishes its progress every kPublish pixels
+#ifndef S2PB_PUBLISH
+#define S2PB_PUBLISH 8        // (a knob for A/B builds: fewer publications = fewer ld.acquire polls by the next band)
+#endif
+constexpr int kPublish = S2PB_PUBLISH;   // a band publishes its progress every kPublish pixels
 
 // ------------------------------------------------------------------ small helpers
 
