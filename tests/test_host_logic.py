@@ -164,3 +164,12 @@ def test_gloo_two_ranks_shard_and_gather(tmp_path):
     out = subprocess.run(["python", "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
                           "127.0.0.1", "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert "GATHER_OK 6" in out.stdout, out.stdout + out.stderr
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/s2pb200.h is the C ABI: it must compile as C99 on its own (no C++, no CUDA, no torch types)."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "s2pb200.h"\nint main(void) { s2pb_mgm_params p; s2pb_rpc r; (void)p; (void)r; return S2PB_OK; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                        "-o", str(tmp_path / "hdr.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
