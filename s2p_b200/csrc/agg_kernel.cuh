@@ -137,6 +137,28 @@ template <int LPL> __device__ __forceinline__ void st_vec(float *p, const float 
         for (int q = 0; q < LPL; q++) p[q] = v[q];
     }
 }
+// the pass volumes are written once and read back gigabytes later: S2PB_STREAM_STORES=1 (an A/B build knob, off by
+// default) marks their stores evict-first so that they do not displace the cost rows and band hand-off rows in L2
+#ifndef S2PB_STREAM_STORES
+#define S2PB_STREAM_STORES 0
+#endif
+template <int LPL> __device__ __forceinline__ void st_vec_out(float *p, const float (&v)[LPL])
+{
+#if S2PB_STREAM_STORES
+    if constexpr (LPL % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < LPL / 4; q++) __stcs(reinterpret_cast<float4 *>(p) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    } else if constexpr (LPL % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < LPL / 2; q++) __stcs(reinterpret_cast<float2 *>(p) + q, make_float2(v[2 * q], v[2 * q + 1]));
+    } else {
+#pragma unroll
+        for (int q = 0; q < LPL; q++) __stcs(p + q, v[q]);
+    }
+#else
+    st_vec<LPL>(p, v);
+#endif
+}
 // raw f16 bits of a lane's LPL costs
 template <int LPL> struct HalfPack { unsigned short h[LPL]; };
 template <int LPL> __device__ __forceinline__ HalfPack<LPL> ld_cost(const __half *p)
@@ -588,7 +610,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
                 for (int e = 0; e < LPL; e++) hNew.v[e] = LA[e];
                 hNew.m = mAm;
                 fill_edges<LPL>(hNew, lane);
-                st_vec<LPL>(outA, LA);
+                st_vec_out<LPL>(outA, LA);
                 outA += lstep;
             }
             if (actB) {
@@ -597,7 +619,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
                 wAB.m = mBm;
                 if (useA) fill_edges<LPL>(wAB, lane);
                 if (usePrev) st_vec<LPL>(myring + (iB & (kRing - 1)) * DP, LB);
-                st_vec<LPL>(outB, LB);
+                st_vec_out<LPL>(outB, LB);
                 outB += lstep;
                 if (lane == 0 && usePrev) myringm[iB & (kRing - 1)] = mBm;
                 if (publish) {

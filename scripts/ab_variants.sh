@@ -3,7 +3,7 @@
 #   bash scripts/ab_variants.sh build      (in the CPU container: builds s2p_b200/libs2pb200_<name>.so for every variant)
 #   bash scripts/ab_variants.sh run        (on the GPU box: one bench line per library, default first)
 # Remove the variant libraries afterwards (they travel with every gpurun snapshot): bash scripts/ab_variants.sh clean
-VARIANTS="split:-DS2PB_SPLIT_LOOP=1 pub16:-DS2PB_PUBLISH=16 pub32:-DS2PB_PUBLISH=32"
+VARIANTS="split:-DS2PB_SPLIT_LOOP=1 pub16:-DS2PB_PUBLISH=16 pub32:-DS2PB_PUBLISH=32 stream:-DS2PB_STREAM_STORES=1"
 case "$1" in
 build)
   for v in $VARIANTS; do
