@@ -40,10 +40,11 @@ COSTS = ("census", "ad", "sd", "ncc", "btad", "btsd")   # -t, index = OrcParams.
 
 
 def mgm_params(**kw):
-    """Defaults = what s2p sets for algo == 'mgm' (s2p/block_matching.py:155-186)."""
+    """Defaults = what s2p sets for algo == 'mgm' (s2p/block_matching.py:155-186).  dct_shift=1: the matched image goes
+    through the reference's DCT round trip even at shift 0 (mgm_costvolume.cc:23-60), like the binary; 0 = identity."""
     d = dict(ndir=8, tsgm=3, census_win=5, P1=8.0, P2=32.0, median=1, lr_mode=1, lr_tau=1.0,
              mindiff=-1.0, remove_small_cc=0, subpix=1, scales=-1, refine=1, fix_overcount=1,
-             dct_shift=0, cost=0)
+             dct_shift=1, cost=0)
     d.update(kw)
     return OrcParams(**d)
 
@@ -52,7 +53,7 @@ def mgm_multi_params(**kw):
     """Defaults = what s2p sets for algo == 'mgm_multi' (s2p/block_matching.py:269-308)."""
     d = dict(ndir=8, tsgm=4, census_win=5, P1=8.0, P2=32.0, median=0, lr_mode=1, lr_tau=1.0,
              mindiff=-1.0, remove_small_cc=25, subpix=2, scales=6, refine=1, fix_overcount=1,
-             dct_shift=0, cost=0)
+             dct_shift=1, cost=0)
     d.update(kw)
     return OrcParams(**d)
 
@@ -94,7 +95,7 @@ class port:
         return out
 
     @staticmethod
-    def costvolume(u, v, lo, hi, gmin, D, win=5, zoom=1, dct_shift=0, cost=0):
+    def costvolume(u, v, lo, hi, gmin, D, win=5, zoom=1, dct_shift=1, cost=0):
         """cost: index into COSTS, or its name"""
         u, v = _f32(u), _f32(v)
         h, w = u.shape

@@ -10,6 +10,9 @@
  * cos()-per-term shim).
  */
 #include "fftw3.h"
+#ifndef S2PB_FFTW_ALT
+#define S2PB_FFTW_ALT 0   /* 1, 2: alternative summation orders, only for oracle/_ref/mgm_alt{1,2} (scripts/nodata_spread.py) */
+#endif
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -76,9 +79,19 @@ void fftw_execute(const fftw_plan p)
     double *restrict y = p->out;
     for (int k = 0; k < n; k++) {
         const double *restrict row = p->table + (size_t)k * n;
+#if S2PB_FFTW_ALT == 1      /* same products, summed from the far end: "another fftw build" for the spread study */
+        double acc = 0.0;
+        for (int j = n - 1; j >= 0; j--) acc += row[j] * x[j];
+        y[k] = acc;
+#elif S2PB_FFTW_ALT == 2    /* 80-bit accumulation, rounded once: a near-exact transform */
+        long double acc = 0.0L;
+        for (int j = 0; j < n; j++) acc += (long double)row[j] * (long double)x[j];
+        y[k] = (double)acc;
+#else
         double acc = 0.0;
         for (int j = 0; j < n; j++) acc += row[j] * x[j];
         y[k] = acc;
+#endif
     }
 }
 

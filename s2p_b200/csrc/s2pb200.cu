@@ -7,6 +7,7 @@
 #include "../../include/s2pb200.h"
 #include "mgm_kernels.cuh"
 #include "multiscale_kernels.cuh"
+#include "dct_kernels.cuh"
 #include "homography_kernels.cuh"
 #include "fusion_kernels.cuh"
 #include "triangulation_kernels.cuh"
@@ -49,6 +50,11 @@ static int fail(int code, const char *fmt, ...)
 
 struct ViewWS {
     float *img;            // NaN-free copy
+    float *rt;             // ... after the reference's DCT round trip (what the OTHER view's cost volume matches against)
+    uint64_t *census_rt;   // census (or NCC window statistics) of rt
+    int *rowlist;          // rows the round trip had to transform
+    float *rowthr;         // per row: pixels with |x| <= rowthr are recomputed (-1: none)
+    RtState *rtstate;
     short *lo, *hi;        // per-pixel label range
     uint64_t *census;
     void *C;               // [H][W][DP] costs: __half (census popcounts) or float (general flavour)
@@ -65,6 +71,7 @@ struct Slot {
     ViewWS v[2];
     int *next_item = nullptr;
     float *lut = nullptr;
+    double *Ydct = nullptr;       // [H][W] DCT coefficients of the rows in flight (dct_kernels.cuh)
     // staging for the host-buffer API
     float *d_in[2] = {nullptr, nullptr};
     float *d_w[2] = {nullptr, nullptr};           // -wl / -wr weight images of s2pb_mgm_weighted
@@ -93,6 +100,9 @@ struct s2pb_ctx {
     int *scratch_flag = nullptr;   // pinned + mapped: device -> host one-word answers
     int *d_scratch = nullptr;      // 64 words of device memory (hull accumulators of mgm_multi)
     long long launches = 0;
+    // DCT coefficient tables of the matched image's round trip, one entry per image width (dct_tables)
+    struct DctTab { int n; double *T10, *T01t, *T01, *TR01, *mc, *ms; };
+    std::vector<DctTab> dct;
     // scratch pool of the warp / stage entry points: device buffers are kept between calls
     struct PoolBuf { void *p; size_t bytes; bool used; };
     std::vector<PoolBuf> pool;
@@ -137,6 +147,11 @@ static int slot_layout(Slot &s, int w, int h, int DP, int ndir, int cbytes, bool
         o = take(npix * 2); if (allocate) v.lo = (short *)(b + o);
         o = take(npix * 2); if (allocate) v.hi = (short *)(b + o);
         o = take(npix * 8); if (allocate) v.census = (uint64_t *)(b + o);
+        o = take(npix * 4); if (allocate) v.rt = (float *)(b + o);
+        o = take(npix * 8); if (allocate) v.census_rt = (uint64_t *)(b + o);
+        o = take((size_t)h * 4); if (allocate) v.rowlist = (int *)(b + o);
+        o = take((size_t)h * 4); if (allocate) v.rowthr = (float *)(b + o);
+        o = take(256); if (allocate) v.rtstate = (RtState *)(b + o);
         o = take(npix * DP * cbytes); if (allocate) v.C = (void *)(b + o);
         for (int p = 0; p < ndir; p++) {
             o = take(npix * DP * 4); if (allocate) v.L[p] = (float *)(b + o);
@@ -151,6 +166,7 @@ static int slot_layout(Slot &s, int w, int h, int DP, int ndir, int cbytes, bool
     size_t o;
     o = take(256); if (allocate) s.next_item = (int *)(b + o);
     o = take(256); if (allocate) s.lut = (float *)(b + o);
+    o = take(npix * 8); if (allocate) s.Ydct = (double *)(b + o);
     if (!allocate) s.bytes = off;
     return 0;
 }
@@ -276,6 +292,7 @@ extern "C" void s2pb_destroy(s2pb_ctx *ctx)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (auto &b : ctx->pool) cudaFree(b.p);
+    for (auto &t : ctx->dct) for (double *q : {t.T10, t.T01t, t.T01, t.TR01, t.mc, t.ms}) if (q) cudaFree(q);
     if (ctx->abort_flag) cudaFreeHost(ctx->abort_flag);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     delete ctx;
@@ -520,6 +537,100 @@ static void fill_wta(WtaParams &P, const ViewWS &v, int ndir, int gmin, const s2
     P.disp = v.disp; P.cost = v.cost; P.conf = v.conf;
 }
 
+// ------------------------------------------------------------------ the matched image's DCT round trip (dct_kernels.cuh)
+
+// Coefficient tables for rows of n pixels, computed once per width on the host (libm, like the reference's DCT) and
+// kept on the device.  FFTW's unnormalised definitions:
+//   REDFT10  Y[k] = sum_j 2 cos(pi (j + 1/2) k / n) X[j]
+//   REDFT01  Y[i] = X[0] + sum_{k>=1} 2 cos(pi k (i + 1/2) / n) X[k]
+//   RODFT01  Y[i] = (-1)^i X[n-1] + sum_{k<n-1} 2 sin(pi (k + 1) (i + 1/2) / n) X[k]
+// half = true adds what the half-pixel shift of SUBPIX = 2 needs (both inverse tables row-major and the phase factors
+// cos(k a), sin(k a), a = (pi / n) * (-1/2), shear.c:66-79).
+static int dct_tables(s2pb_ctx *ctx, int n, bool half, const s2pb_ctx::DctTab **out)
+{
+    if (n > 8192) return fail(S2PB_ERR_UNSUPPORTED, "tiles wider than 8192 px are not supported (DCT tables of %d x %d doubles)", n, n);
+    s2pb_ctx::DctTab *t = nullptr;
+    for (auto &e : ctx->dct) if (e.n == n) t = &e;
+    if (!t) { ctx->dct.push_back({n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}); t = &ctx->dct.back(); }
+    const double pi = 3.14159265358979323846264338327950288;
+    const size_t nn = (size_t)n * n;
+    std::vector<double> h;
+    auto upload = [&](double **dst, size_t count) -> int {
+        cudaError_t e = cudaMalloc((void **)dst, count * sizeof(double));
+        if (e != cudaSuccess) { cudaGetLastError(); *dst = nullptr; return fail(S2PB_ERR_NOMEM, "DCT table of %zu bytes: %s", count * 8, cudaGetErrorString(e)); }
+        CK(cudaMemcpy(*dst, h.data(), count * sizeof(double), cudaMemcpyHostToDevice));
+        return S2PB_OK;
+    };
+    int rc;
+    if (!t->T10) {
+        h.resize(nn);
+        for (int k = 0; k < n; k++)
+            for (int j = 0; j < n; j++) h[(size_t)k * n + j] = 2.0 * cos(pi * (j + 0.5) * k / n);
+        if ((rc = upload(&t->T10, nn)) != S2PB_OK) return rc;
+    }
+    if (!half && !t->T01t) {     // transposed: [k][i]
+        h.resize(nn);
+        for (int k = 0; k < n; k++)
+            for (int i = 0; i < n; i++) h[(size_t)k * n + i] = (k == 0) ? 1.0 : 2.0 * cos(pi * k * (i + 0.5) / n);
+        if ((rc = upload(&t->T01t, nn)) != S2PB_OK) return rc;
+    }
+    if (half && !t->T01) {
+        h.resize(nn);
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < n; k++) h[(size_t)i * n + k] = (k == 0) ? 1.0 : 2.0 * cos(pi * k * (i + 0.5) / n);
+        if ((rc = upload(&t->T01, nn)) != S2PB_OK) return rc;
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < n; k++) h[(size_t)i * n + k] = (k == n - 1) ? ((i & 1) ? -1.0 : 1.0) : 2.0 * sin(pi * (k + 1) * (i + 0.5) / n);
+        if ((rc = upload(&t->TR01, nn)) != S2PB_OK) return rc;
+        const float q = 0.5f, translation = -q;                  // shift() passes (0., -q) as floats, mgm_costvolume.cc:35
+        const double tt = 0 * 0.0f + translation, a = (M_PI / n) * tt;
+        h.resize(n);
+        for (int k = 0; k < n; k++) h[k] = cos(k * a);
+        if ((rc = upload(&t->mc, n)) != S2PB_OK) return rc;
+        for (int k = 0; k < n; k++) h[k] = sin(k * a);
+        if ((rc = upload(&t->ms, n)) != S2PB_OK) return rc;
+    }
+    *out = t;
+    return S2PB_OK;
+}
+
+// rt = shift(img, 0) of the reference: see dct_kernels.cuh.  Asynchronous; when no row needs it the three kernels return
+// at once.  Y: [h][w] doubles of scratch.
+static int round_trip_zero(s2pb_ctx *ctx, const float *img, int w, int h, float *rt, RtState *state, int *rowlist, float *rowthr,
+                           double *Y, cudaStream_t st)
+{
+    const s2pb_ctx::DctTab *t;
+    int rc = dct_tables(ctx, w, false, &t);
+    if (rc != S2PB_OK) return rc;
+    static bool configured = false;
+    if (!configured) { CK(cudaFuncSetAttribute(rt_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); configured = true; }
+    CK(cudaMemsetAsync(state, 0, sizeof(RtState), st));
+    rt_flag_kernel<<<h, 256, 0, st>>>(img, w, h, rt, state, rowlist, rowthr);
+    dct_gemm_kernel<float, true><<<ctx->sm_count * 3, 256, 0, st>>>(t->T10, img, w, h, state, rowlist, Y, nullptr, nullptr, nullptr);
+    rt_inverse_kernel<<<ctx->sm_count * 4, 256, (size_t)w * sizeof(double), st>>>(t->T01t, Y, w, state, rowlist, rowthr, img, rt);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    return S2PB_OK;
+}
+
+// out = shift(img, 1/2) of the reference (SUBPIX = 2).  scratch: 4 x [h][w] doubles.
+static int shift_half(s2pb_ctx *ctx, const float *img, int w, int h, float *out, double *scratch, cudaStream_t st)
+{
+    const s2pb_ctx::DctTab *t;
+    int rc = dct_tables(ctx, w, true, &t);
+    if (rc != S2PB_OK) return rc;
+    const size_t npix = (size_t)w * h;
+    double *ck = scratch, *sk = scratch + npix, *sym = scratch + 2 * npix, *anti = scratch + 3 * npix;
+    const int g = ctx->sm_count * 3;
+    dct_gemm_kernel<float, true><<<g, 256, 0, st>>>(t->T10, img, w, h, nullptr, nullptr, ck, t->mc, t->ms, sk);
+    dct_gemm_kernel<double, false><<<g, 256, 0, st>>>(t->T01, ck, w, h, nullptr, nullptr, sym, nullptr, nullptr, nullptr);
+    dct_gemm_kernel<double, false><<<g, 256, 0, st>>>(t->TR01, sk, w, h, nullptr, nullptr, anti, nullptr, nullptr, nullptr);
+    dct_combine_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(sym, anti, npix, out);
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    return S2PB_OK;
+}
+
 // ------------------------------------------------------------------ mgm_multi (device level)
 
 static int arena_reset(Slot &s, size_t need)
@@ -602,7 +713,14 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
     }
     float *tl = arena_take<float>(s, npix), *tr = arena_take<float>(s, npix);
     int *lab = arena_take<int>(s, npix), *area = arena_take<int>(s, npix);
-    if (!area) return fail(S2PB_ERR_NOMEM, "pyramid arena exhausted");
+    // the matched images after the reference's DCT round trip (shift 0) and their census / window statistics
+    float *rt[2]; uint64_t *cen_rt[2]; int *rowlist[2]; float *rowthr[2]; RtState *rtstate[2];
+    for (int vi = 0; vi < 2; vi++) {
+        rt[vi] = arena_take<float>(s, npix); cen_rt[vi] = arena_take<uint64_t>(s, npix);
+        rowlist[vi] = arena_take<int>(s, h); rowthr[vi] = arena_take<float>(s, h); rtstate[vi] = arena_take<RtState>(s, 1);
+    }
+    double *dscratch = arena_take<double>(s, npix * (zoom == 2 ? 4 : 1));
+    if (!dscratch) return fail(S2PB_ERR_NOMEM, "pyramid arena exhausted");
     // hull accumulators live in device memory (atomics on mapped host memory need PCIe atomics); copied back once
     int *d_hull = ctx->d_scratch;
     const int hull_init[4] = {0x7fffffff, (int)0x80000000, 0x7fffffff, (int)0x80000000};
@@ -632,16 +750,18 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
     // ---- census (and, for ZOOMFACTOR 2, of the half-pixel shifted matched images)
     const float *img[2] = {L.u, L.v};
     float *shf[2] = {shifted, shifted1};       // shf[vi] = shift(img[vi], 1/2) (kept for the image-domain distances)
-    if (census) {
-        for (int vi = 0; vi < 2; vi++) {
-            census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(img[vi], w, h, p->census_win / 2, s.v[vi].census);
+    for (int vi = 0; vi < 2; vi++) {          // rt[vi] = shift(img[vi], 0): what the other view's labels of shift 0 match against
+        rc = round_trip_zero(ctx, img[vi], w, h, rt[vi], rtstate[vi], rowlist[vi], rowthr[vi], dscratch, st);
+        if (rc != S2PB_OK) return rc;
+        if (census) {
+            census_pair_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(img[vi], rt[vi], rtstate[vi], w, h, p->census_win / 2, s.v[vi].census, cen_rt[vi]);
             ctx->launches++;
         }
     }
     if (zoom == 2) {
         for (int vi = 0; vi < 2; vi++) {      // cen_half[vi] = census(shift(img[vi], 1/2))
-            dct_shift_kernel<<<h, 256, (size_t)7 * w * sizeof(double), st>>>(img[vi], shf[vi], w, 0.5f);
-            ctx->launches++;
+            rc = shift_half(ctx, img[vi], w, h, shf[vi], dscratch, st);
+            if (rc != S2PB_OK) return rc;
             if (census) { census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(shf[vi], w, h, p->census_win / 2, cen_half[vi]); ctx->launches++; }
         }
     }
@@ -649,7 +769,8 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
     if (ncc) {
         for (int vi = 0; vi < 2; vi++) {
             ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(img[vi], w, h, p->census_win / 2, (float2 *)s.v[vi].census);
-            ctx->launches++;
+            ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(rt[vi], w, h, p->census_win / 2, (float2 *)cen_rt[vi]);
+            ctx->launches += 2;
             if (zoom == 2) { ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(shf[vi], w, h, p->census_win / 2, (float2 *)cen_half[vi]); ctx->launches++; }
         }
     }
@@ -659,22 +780,22 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
         if (general) {
             CostGenParams G;
             memset(&G, 0, sizeof G);
-            G.u = img[vi]; G.v0 = img[1 - vi]; G.v1 = zoom == 2 ? shf[1 - vi] : nullptr;
-            G.cu = s.v[vi].census; G.cv0 = s.v[1 - vi].census; G.cv1 = zoom == 2 ? cen_half[1 - vi] : nullptr;
+            G.u = img[vi]; G.v0 = rt[1 - vi]; G.v1 = zoom == 2 ? shf[1 - vi] : nullptr;
+            G.cu = s.v[vi].census; G.cv0 = cen_rt[1 - vi]; G.cv1 = zoom == 2 ? cen_half[1 - vi] : nullptr;
             G.su = (const float2 *)G.cu; G.sv0 = (const float2 *)G.cv0; G.sv1 = (const float2 *)G.cv1;
             G.lut = s.lut; G.lo = lo[vi]; G.hi = hi[vi];
             G.w = w; G.h = h; G.gmin = gminv[vi]; G.cost = p->cost; G.win = p->census_win; G.zoom = zoom;
             G.C = (float *)s.v[vi].C;
             rc = launch_cost_gen(ctx, LPL, G, st);
         } else if (chunked_mode() == 1 && chunked_enabled(32 * LPL)) {      // experimental: only the chunks of each pixel's span
-            if (zoom == 2) cost_chunked_kernel<true><<<ctx->sm_count * 8, 256, 0, st>>>(s.v[vi].census, s.v[1 - vi].census, cen_half[1 - vi], w, h,
+            if (zoom == 2) cost_chunked_kernel<true><<<ctx->sm_count * 8, 256, 0, st>>>(s.v[vi].census, cen_rt[1 - vi], cen_half[1 - vi], w, h,
                                                                                   lo[vi], hi[vi], gminv[vi], 32 * LPL, (__half *)s.v[vi].C);
-            else cost_chunked_kernel<false><<<ctx->sm_count * 8, 256, 0, st>>>(s.v[vi].census, s.v[1 - vi].census, nullptr, w, h,
+            else cost_chunked_kernel<false><<<ctx->sm_count * 8, 256, 0, st>>>(s.v[vi].census, cen_rt[1 - vi], nullptr, w, h,
                                                                                lo[vi], hi[vi], gminv[vi], 32 * LPL, (__half *)s.v[vi].C);
             ctx->launches++;
             rc = cudaGetLastError() == cudaSuccess ? S2PB_OK : fail(S2PB_ERR_CUDA, "cost_chunked_kernel launch failed");
         } else {
-            rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census, w, h, lo[vi], hi[vi], gminv[vi], s.v[vi].C, st,
+            rc = launch_cost(ctx, LPL, s.v[vi].census, cen_rt[1 - vi], w, h, lo[vi], hi[vi], gminv[vi], s.v[vi].C, st,
                              zoom == 2 ? cen_half[1 - vi] : nullptr, zoom);
         }
         if (rc != S2PB_OK) return rc;
@@ -746,7 +867,7 @@ static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const f
     }
     size_t need = 0;
     for (auto &L : lv) need += (size_t)L.w * L.h * 4 * 11 + 11 * 256;
-    need += (size_t)n * (4 * 12 + 2 * 4 + 8 * 2 + 4 * 2) * 2 + (1 << 20);     // scratch of the mgm_calls (two at full size)
+    need += (size_t)n * (4 * 12 + 2 * 4 + 8 * 2 + 4 * 2 + (4 + 8) * 2 + 8 * 4) * 2 + (1 << 20);     // scratch of the mgm_calls (two at full size)
     int rc = arena_reset(s, need);
     if (rc != S2PB_OK) return rc;
     for (auto &L : lv) {
@@ -885,10 +1006,18 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
         int lo_all = vi == 0 ? dmin : -dmax, hi_all = vi == 0 ? dmax : -dmin;
         prepare_view_kernel<<<(n + 255) / 256, 256, 0, st>>>(im[vi], n, lo_all, hi_all, dmin, s.v[vi].img, s.v[vi].lo, s.v[vi].hi);
         ctx->launches++;
-        if (census) { census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].img, w, h, p->census_win / 2, s.v[vi].census); ctx->launches++; }
-        if (p->cost == S2PB_COST_NCC) {     // window statistics in the (then unused) census buffer: 8 B / pixel
-            ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].img, w, h, p->census_win / 2, (float2 *)s.v[vi].census);
+        // the copy the OTHER view matches against goes through the reference's DCT round trip (mgm_costvolume.cc:50-60)
+        rc = round_trip_zero(ctx, s.v[vi].img, w, h, s.v[vi].rt, s.v[vi].rtstate, s.v[vi].rowlist, s.v[vi].rowthr, s.Ydct, st);
+        if (rc != S2PB_OK) return rc;
+        if (census) {
+            census_pair_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].img, s.v[vi].rt, s.v[vi].rtstate, w, h, p->census_win / 2,
+                                                               s.v[vi].census, s.v[vi].census_rt);
             ctx->launches++;
+        }
+        if (p->cost == S2PB_COST_NCC) {     // window statistics in the (then unused) census buffers: 8 B / pixel
+            ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].img, w, h, p->census_win / 2, (float2 *)s.v[vi].census);
+            ncc_stats_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(s.v[vi].rt, w, h, p->census_win / 2, (float2 *)s.v[vi].census_rt);
+            ctx->launches += 2;
         }
     }
     CK(cudaGetLastError());
@@ -898,15 +1027,15 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
         if (general) {
             CostGenParams G;
             memset(&G, 0, sizeof G);
-            G.u = s.v[vi].img; G.v0 = s.v[1 - vi].img;
-            G.cu = s.v[vi].census; G.cv0 = s.v[1 - vi].census;
+            G.u = s.v[vi].img; G.v0 = s.v[1 - vi].rt;
+            G.cu = s.v[vi].census; G.cv0 = s.v[1 - vi].census_rt;
             G.su = (const float2 *)G.cu; G.sv0 = (const float2 *)G.cv0;
             G.lut = s.lut; G.lo = s.v[vi].lo; G.hi = s.v[vi].hi;
             G.w = w; G.h = h; G.gmin = gminv[vi]; G.cost = p->cost; G.win = p->census_win; G.zoom = 1;
             G.C = (float *)s.v[vi].C;
             rc = launch_cost_gen(ctx, LPL, G, st);
         } else {
-            rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census, w, h, s.v[vi].lo, s.v[vi].hi, gminv[vi], s.v[vi].C, st);
+            rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census_rt, w, h, s.v[vi].lo, s.v[vi].hi, gminv[vi], s.v[vi].C, st);
         }
         if (rc != S2PB_OK) return rc;
     }
@@ -1170,6 +1299,19 @@ struct DevBuf {
 };
 #define ALLOC(buf, n) do { if ((buf).alloc(n) != 0) { cudaGetLastError(); return fail(S2PB_ERR_NOMEM, "cudaMalloc of %zu bytes failed", (size_t)(n)); } } while (0)
 
+// the stage entry points take the matched image as the caller has it and apply the reference's round trip themselves
+// (allocate_and_fill_sgm_costvolume does, mgm_costvolume.cc:94): dv is replaced by shift(dv, 0) in place
+static int stage_round_trip(s2pb_ctx *ctx, DevBuf &dv, int w, int h, cudaStream_t st, DevBuf &rt, DevBuf &aux, DevBuf &Y)
+{
+    size_t npix = (size_t)w * h;
+    ALLOC(rt, npix * 4); ALLOC(aux, (size_t)h * 8 + 256); ALLOC(Y, npix * 8);
+    int rc = round_trip_zero(ctx, dv.as<float>(), w, h, rt.as<float>(), (RtState *)(aux.as<char>() + (size_t)h * 8), aux.as<int>(),
+                             (float *)(aux.as<char>() + (size_t)h * 4), Y.as<double>(), st);
+    if (rc != S2PB_OK) return rc;
+    void *t = dv.p; dv.p = rt.p; rt.p = t;
+    return S2PB_OK;
+}
+
 extern "C" int s2pb_census(s2pb_ctx *ctx, const float *img, int w, int h, int win, uint64_t *codes)
 {
     if (!ctx || !img || !codes || w < 1 || h < 1) return fail(S2PB_ERR_ARG, "bad argument");
@@ -1221,6 +1363,9 @@ extern "C" int s2pb_costvolume(s2pb_ctx *ctx, const float *u, const float *v, in
     if (rc != S2PB_OK) return rc;
     CK(cudaMemcpyAsync(du.p, u, npix * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dv.p, v, npix * 4, cudaMemcpyHostToDevice, st));
+    DevBuf rtb, rtaux, rtY;
+    rc = stage_round_trip(ctx, dv, w, h, st, rtb, rtaux, rtY);
+    if (rc != S2PB_OK) return rc;
     dim3 b2(32, 8);
     census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(du.as<float>(), w, h, win / 2, cu.as<uint64_t>());
     census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dv.as<float>(), w, h, win / 2, cv.as<uint64_t>());
@@ -1258,6 +1403,9 @@ extern "C" int s2pb_costvolume_dist(s2pb_ctx *ctx, const float *u, const float *
     if (rc != S2PB_OK) return rc;
     CK(cudaMemcpyAsync(du.p, u, npix * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dv.p, v, npix * 4, cudaMemcpyHostToDevice, st));
+    DevBuf rtb, rtaux, rtY;
+    rc = stage_round_trip(ctx, dv, w, h, st, rtb, rtaux, rtY);
+    if (rc != S2PB_OK) return rc;
     float lut_h[64];
     cost_lut(win, lut_h);
     CK(cudaMemcpyAsync(dlut.p, lut_h, 256, cudaMemcpyHostToDevice, st));

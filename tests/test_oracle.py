@@ -46,6 +46,35 @@ def test_identity_shift_equals_dct_shift_without_nodata(oracle, name):
         assert same(dr, g["dispR"])
 
 
+def test_roundtrip_flag_rule(oracle):
+    """The engine only recomputes, through the DCT round trip, the pixels with |x| <= rowmax * n * 2^-24 (rows without such a
+    pixel are left alone): s2p_b200/csrc/dct_kernels.cuh.  Check the claim behind that rule against the full round trip of the
+    oracle: every other pixel returns to its float32 value.  Dynamic ranges from 12-bit imagery to 1e7:1, widths up to 2048."""
+    import ctypes
+    L = oracle.lib()
+    rng = np.random.default_rng(1)
+    changed = 0
+    for n in (64, 200, 777, 1024, 2048):
+        for kind in range(6):
+            h = 12
+            if kind == 0: x = rng.integers(0, 4096, (h, n)).astype(np.float32)
+            elif kind == 1: x = rng.uniform(0, 65535, (h, n)).astype(np.float32)
+            elif kind == 2: x = np.exp(rng.normal(0, 4, (h, n))).astype(np.float32)
+            elif kind == 3: x = rng.uniform(0, 1, (h, n)).astype(np.float32)
+            elif kind == 4: x = (rng.integers(0, 4096, (h, n)) * (rng.random((h, n)) < 0.5)).astype(np.float32)
+            else:
+                x = rng.uniform(-1000, 1000, (h, n)).astype(np.float32)
+                x[:, :n // 10] = 0
+                x[:, -n // 7:] = 0
+            y = np.empty_like(x)
+            L.orc_shift(oracle._p(x), oracle._p(y), n, h, ctypes.c_float(0.0), 1)
+            thr = (np.abs(x).max(axis=1, keepdims=True) * np.float32(n * 2.0 ** -24)).astype(np.float32)
+            unflagged = np.abs(x) > thr
+            assert np.array_equal(y[unflagged], x[unflagged]), (n, kind)
+            changed += int((y != x).sum())
+    assert changed > 1000        # the round trip does move the flagged pixels
+
+
 def _have_ref(oracle):
     return oracle.have_ref()
 
