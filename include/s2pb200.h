@@ -140,7 +140,11 @@ int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh,
 /* ---- n-view merge (a "next" row of SURVEY.md section 8f) ---------------------- */
 /* s2p.fusion.merge_n (s2p/fusion.py:25-68) from memory to memory: out = op_k(inputs[k] - offsets[k]) +
  * mean(offsets), pixelwise in float64, stored as float32.  op: 0 average_if_close (NaN when
- * nanmax - nanmin > threshold, else nanmedian; s2p/fusion.py:16-23), 1 nanmedian, 2 nanmean, 3 nanmin, 4 nanmax. */
+ * nanmax - nanmin > threshold, else nanmedian; s2p/fusion.py:16-23), 1 nanmedian, 2 nanmean, 3 nanmin, 4 nanmax,
+ * 5 median, 6 mean, 7 min, 8 max (the reducers s2p/fusion.py:31-36 names).  OR-ing S2PB_FUSE_SUB_F32 into op performs
+ * the subtraction in float32, which is what `f.read(1) - offsets[i]` does under NumPy < 2 (value-based casting of
+ * the 0-d float64 offset); without it the subtraction is in float64 (NumPy >= 2). */
+#define S2PB_FUSE_SUB_F32 0x100
 int s2pb_merge_n(s2pb_ctx *ctx, const float *const *inputs, const double *offsets, int n, int w, int h,
                  int op, double threshold, float *out);
 

@@ -44,13 +44,15 @@ def image_apply_homography(out, im, H, w, h):
     rw, rh = min(rw, sw - x), min(rh, sh - y)
     if rw <= 0 or rh <= 0:
         raise subprocess.CalledProcessError(1, cmd, output="ERROR: empty roi")
-    src = rio.read_window(im, x, y, rw, rh)
     Hc = H @ np.array([[1, 0, x], [0, 1, y], [0, 0, 1]], dtype=np.float64)
+    res = []
     try:
-        res = get_engine().homography(src, Hc, w, h)
+        for band in range(1, rio.band_count(im) + 1):      # every band, like the binary (main.cpp loops over GetRasterCount):
+            src = rio.read_window(im, x, y, rw, rh, band)  # s2p/__init__.py:276 warps the colour image through this function
+            res.append(get_engine().homography(src, Hc, w, h))
     except S2pbError as e:
         raise subprocess.CalledProcessError(-e.code, cmd, output=str(e)) from e
-    rio.write_float_tiff(out, res)
+    rio.write_float_tiff_bands(out, res)
 
 
 def install():

@@ -100,6 +100,9 @@ struct s2pb_ctx {
     int *scratch_flag = nullptr;   // pinned + mapped: device -> host one-word answers
     int *d_scratch = nullptr;      // 64 words of device memory (hull accumulators of mgm_multi)
     long long launches = 0;
+    // deadline of the matcher call in flight (timeout_ms counted from the API entry; has_deadline = false: none)
+    std::chrono::steady_clock::time_point deadline;
+    bool has_deadline = false;
     // DCT coefficient tables of the matched image's round trip, one entry per image width (dct_tables)
     struct DctTab { int n; double *T10, *T01t, *T01, *TR01, *mc, *ms; };
     std::vector<DctTab> dct;
@@ -333,6 +336,39 @@ static int ensure_slots(s2pb_ctx *ctx, int nslots)
         if (r != S2PB_OK) return r;
     }
     return S2PB_OK;
+}
+
+// ------------------------------------------------------------------ timeouts
+
+// The timeout contract (timeout_ms -> S2PB_ERR_TIMEOUT -> subprocess.TimeoutExpired upstream) counts from the API
+// entry: every host-side wait of a matcher call goes through sync_or_timeout, also the per-level read-backs of mgm_multi.
+static void set_deadline(s2pb_ctx *ctx, long long timeout_ms)
+{
+    ctx->has_deadline = timeout_ms > 0;
+    if (ctx->has_deadline) ctx->deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms);
+}
+// stop everything that is in flight on any slot: raise the abort flag (the persistent aggregation kernels drain), wait
+// for every slot stream -- some of them DMA into the caller's buffers -- then clear the flag
+static void drain_all(s2pb_ctx *ctx, bool abort)
+{
+    if (abort) *(volatile int *)ctx->abort_flag = 1;
+    for (auto &s : ctx->slots) if (s.stream) cudaStreamSynchronize(s.stream);
+    if (abort) *(volatile int *)ctx->abort_flag = 0;
+}
+static int sync_or_timeout(s2pb_ctx *ctx, cudaStream_t st)
+{
+    if (!ctx->has_deadline) { CK(cudaStreamSynchronize(st)); return S2PB_OK; }
+    for (;;) {
+        cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaSuccess) return S2PB_OK;
+        if (e != cudaErrorNotReady) return fail(S2PB_ERR_CUDA, "stream failed: %s", cudaGetErrorString(e));
+        if (std::chrono::steady_clock::now() > ctx->deadline) {
+            drain_all(ctx, true);
+            cudaStreamSynchronize(st);
+            return fail(S2PB_ERR_TIMEOUT, "matcher exceeded its timeout");
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+    }
 }
 
 // ------------------------------------------------------------------ stage launchers
@@ -731,7 +767,8 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
     CK(cudaGetLastError());
     int hull[4];
     CK(cudaMemcpyAsync(hull, d_hull, sizeof hull, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    int rc = sync_or_timeout(ctx, st);
+    if (rc != S2PB_OK) return rc;
     int gminv[2] = {hull[0], hull[2]}, gmaxv[2] = {hull[1], hull[3]};
     int D = 0;
     for (int vi = 0; vi < 2; vi++) {
@@ -740,7 +777,7 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
     }
     int LPL = lpl_for(D);
     if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "a %dx%d level needs %d labels in its dense volume; 512 are supported", w, h, D);
-    int rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir, general ? 4 : 2);
+    rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir, general ? 4 : 2);
     if (rc != S2PB_OK) return rc;
     TRACE(st, "level %dx%d zoom %d: hull L [%d,%d] R [%d,%d] -> LPL %d%s", w, h, zoom, gminv[0], gmaxv[0], gminv[1], gmaxv[1], LPL,
           general ? " (general flavour)" : "");
@@ -982,7 +1019,8 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
         *ctx->scratch_flag = 0;
         has_nan_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_im2, n, ctx->scratch_flag);
         ctx->launches++;
-        CK(cudaStreamSynchronize(st));
+        int rs = sync_or_timeout(ctx, st);
+        if (rs != S2PB_OK) return rs;
         nodata_hint = *(volatile int *)ctx->scratch_flag ? 3 : 0;
     }
     int gminv[2], gmaxv[2];
@@ -1087,26 +1125,8 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
     return S2PB_OK;
 }
 
-// wait for `ev` honouring timeout_ms; on expiry raise the abort flag so that the persistent
-// aggregation kernel drains, then report S2PB_ERR_TIMEOUT (-> subprocess.TimeoutExpired upstream).
-static int wait_with_timeout(s2pb_ctx *ctx, cudaStream_t st, int timeout_ms)
-{
-    if (timeout_ms <= 0) { CK(cudaStreamSynchronize(st)); return S2PB_OK; }
-    auto t0 = std::chrono::steady_clock::now();
-    for (;;) {
-        cudaError_t e = cudaStreamQuery(st);
-        if (e == cudaSuccess) return S2PB_OK;
-        if (e != cudaErrorNotReady) return fail(S2PB_ERR_CUDA, "stream failed: %s", cudaGetErrorString(e));
-        auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
-        if (ms > timeout_ms) {
-            *(volatile int *)ctx->abort_flag = 1;
-            cudaStreamSynchronize(st);
-            *(volatile int *)ctx->abort_flag = 0;
-            return fail(S2PB_ERR_TIMEOUT, "matcher exceeded timeout of %d ms", timeout_ms);
-        }
-        std::this_thread::sleep_for(std::chrono::microseconds(100));
-    }
-}
+// wait for everything enqueued on `st`, honouring the deadline of the call (set_deadline)
+static int wait_with_timeout(s2pb_ctx *ctx, cudaStream_t st) { return sync_or_timeout(ctx, st); }
 
 extern "C" int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, const float *d_im2, int w, int h, int dmin, int dmax,
                                const s2pb_mgm_params *p, float *d_disp, float *d_conf, uint8_t *d_mask, float *d_disp_right,
@@ -1121,9 +1141,10 @@ extern "C" int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, cons
     if (rc != S2PB_OK) return rc;
     Slot &s = ctx->slots[slot];
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    set_deadline(ctx, p->timeout_ms);
     rc = mgm_enqueue(ctx, s, d_im1, d_im2, w, h, dmin, dmax, p, d_disp, d_conf, d_mask, d_disp_right, st, nodata_hint);
     if (rc != S2PB_OK) return rc;
-    if (p->timeout_ms > 0) return wait_with_timeout(ctx, st, p->timeout_ms);
+    if (p->timeout_ms > 0) return wait_with_timeout(ctx, st);
     return S2PB_OK;
 }
 
@@ -1197,9 +1218,10 @@ extern "C" int s2pb_mgm_weighted(s2pb_ctx *ctx, const float *im1, const float *i
     if (rc != S2PB_OK) return rc;
     CK(cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[0];
+    set_deadline(ctx, p->timeout_ms);
     rc = mgm_host_enqueue(ctx, s, im1, im2, w, h, dmin, dmax, p, mask != nullptr, disp_right != nullptr, disp, conf, mask, wl, wr);
-    if (rc != S2PB_OK) return rc;
-    rc = wait_with_timeout(ctx, s.stream, p->timeout_ms);
+    if (rc != S2PB_OK) { cudaStreamSynchronize(s.stream); return rc; }      // nothing may still DMA into the caller's buffers
+    rc = wait_with_timeout(ctx, s.stream);
     if (rc != S2PB_OK) return rc;
     size_t npix = (size_t)w * h;
     if (!s.direct_out) {
@@ -1240,18 +1262,12 @@ extern "C" int s2pb_mgm_batch(s2pb_ctx *ctx, int n, const float *const *im1, con
     const int ns = (int)ctx->slots.size();
     const size_t npix = (size_t)w * h;
     std::vector<int> inflight(ns, -1);
-    auto t0 = std::chrono::steady_clock::now();
+    set_deadline(ctx, p->timeout_ms * (long long)(n > 0 ? n : 1));       // the per-tile timeout times the number of tiles
     auto collect = [&](int si) -> int {
         Slot &s = ctx->slots[si];
         int t = inflight[si];
         if (t < 0) return S2PB_OK;
-        int left = 0;
-        if (p->timeout_ms > 0) {
-            auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
-            left = (int)(p->timeout_ms * (long long)(n > 0 ? n : 1) - ms);
-            if (left < 1) left = 1;
-        }
-        int r = wait_with_timeout(ctx, s.stream, left);
+        int r = wait_with_timeout(ctx, s.stream);
         if (r != S2PB_OK) return r;
         if (!s.direct_out) {
             memcpy(disp[t], s.h_disp, npix * 4);
@@ -1261,18 +1277,21 @@ extern "C" int s2pb_mgm_batch(s2pb_ctx *ctx, int n, const float *const *im1, con
         inflight[si] = -1;
         return S2PB_OK;
     };
+    // on any error the other slots still have kernels and copies in flight, some of them into the caller's page-locked
+    // buffers: stop and wait for all of them before returning (the caller may free its arrays right away)
+    auto bail = [&](int code) -> int { std::string keep = g_err; drain_all(ctx, true); g_err = keep; return code; };
     for (int t = 0; t < n; t++) {
         int si = t % ns;
         rc = collect(si);
-        if (rc != S2PB_OK) return rc;
+        if (rc != S2PB_OK) return bail(rc);
         rc = mgm_host_enqueue(ctx, ctx->slots[si], im1[t], im2[t], w, h, dmin, dmax, p, mask && mask[t], false, disp[t], conf[t],
                               mask ? mask[t] : nullptr);
-        if (rc != S2PB_OK) return rc;
+        if (rc != S2PB_OK) return bail(rc);
         inflight[si] = t;
     }
     for (int k = 0; k < ns; k++) {
         rc = collect((n + k) % ns);
-        if (rc != S2PB_OK) return rc;
+        if (rc != S2PB_OK) return bail(rc);
     }
     return S2PB_OK;
 }
@@ -1769,7 +1788,9 @@ extern "C" int s2pb_merge_n(s2pb_ctx *ctx, const float *const *inputs, const dou
 {
     if (!ctx || !inputs || !offsets || !out || n < 1 || w < 1 || h < 1) return fail(S2PB_ERR_ARG, "bad argument");
     if (n > kMaxFusion) return fail(S2PB_ERR_UNSUPPORTED, "at most %d rasters can be merged", kMaxFusion);
-    if (op < FUSE_AVERAGE_IF_CLOSE || op > FUSE_NANMAX) return fail(S2PB_ERR_ARG, "unknown averaging operator %d", op);
+    const int sub_f32 = (op & S2PB_FUSE_SUB_F32) ? 1 : 0;
+    op &= ~S2PB_FUSE_SUB_F32;
+    if (op < FUSE_AVERAGE_IF_CLOSE || op >= FUSE_OP_COUNT) return fail(S2PB_ERR_ARG, "unknown averaging operator %d", op);
     CK(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)w * h;
     cudaStream_t st = ctx->slots[0].stream;
@@ -1786,7 +1807,7 @@ extern "C" int s2pb_merge_n(s2pb_ctx *ctx, const float *const *inputs, const dou
         P.offset[k] = offsets[k];
         s += offsets[k];                     // np.mean of a short list: plain left-to-right sum / n
     }
-    P.n = n; P.op = op; P.threshold = threshold; P.mean_offset = s / n; P.npix = npix; P.out = o.as<float>();
+    P.n = n; P.op = op; P.sub_f32 = sub_f32; P.threshold = threshold; P.mean_offset = s / n; P.npix = npix; P.out = o.as<float>();
     fusion_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(P);
     ctx->launches++;
     CK(cudaGetLastError());

@@ -158,21 +158,32 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ n-view merge
-    FUSION_OPS = {"average_if_close": 0, "np.nanmedian": 1, "np.nanmean": 2, "np.nanmin": 3, "np.nanmax": 4}
+    FUSION_OPS = {"average_if_close": 0, "np.nanmedian": 1, "np.nanmean": 2, "np.nanmin": 3, "np.nanmax": 4,
+                  "np.median": 5, "np.mean": 6, "np.min": 7, "np.max": 8, "np.amin": 7, "np.amax": 8}
+    FUSE_SUB_F32 = 0x100
 
-    def merge_n(self, rasters, offsets, averaging="average_if_close", threshold=1.0):
-        """Pixelwise merge of n equally sized rasters (s2p/fusion.py:25-68) -> float32 array."""
+    @staticmethod
+    def numpy_subtracts_in_float32():
+        """How `f.read(1) - offsets[i]` (s2p/fusion.py:49: float32 raster minus the 0-d float64 array np.loadtxt returned)
+        is evaluated by the NumPy in this environment: float32 under value-based casting (NumPy < 2), float64 under NEP 50."""
+        return (np.zeros(1, np.float32) - np.array(1.5)).dtype == np.float32
+
+    def merge_n(self, rasters, offsets, averaging="average_if_close", threshold=1.0, sub_f32=None):
+        """Pixelwise merge of n equally sized rasters (s2p/fusion.py:25-68) -> float32 array.
+        sub_f32: subtract the offsets in float32 (NumPy < 2 semantics) or float64; None = what this NumPy does."""
         if averaging.startswith("numpy."):
             averaging = "np." + averaging[6:]
         if averaging not in self.FUSION_OPS:
-            raise NotImplementedError("averaging operator %r" % averaging)
+            raise NotImplementedError("averaging operator %r (supported: %s)" % (averaging, ", ".join(sorted(self.FUSION_OPS))))
+        if sub_f32 is None:
+            sub_f32 = self.numpy_subtracts_in_float32()
         rs = [_f32(r) for r in rasters]
         n = len(rs)
         h, w = rs[0].shape
         ptrs = (ctypes.c_void_p * n)(*[r.ctypes.data for r in rs])
         offs = (ctypes.c_double * n)(*[float(o) for o in offsets])
         out = np.empty((h, w), np.float32)
-        _lib.check(self._L.s2pb_merge_n(self._ctx, ptrs, offs, n, w, h, self.FUSION_OPS[averaging], float(threshold), _fp(out)))
+        _lib.check(self._L.s2pb_merge_n(self._ctx, ptrs, offs, n, w, h, self.FUSION_OPS[averaging] | (self.FUSE_SUB_F32 if sub_f32 else 0), float(threshold), _fp(out)))
         return out
 
     def erode_mask(self, mask, radius=2):

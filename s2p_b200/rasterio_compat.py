@@ -20,6 +20,11 @@ def read_band(path):
     if _HAVE_RASTERIO:
         with rasterio.open(path, "r") as f:
             return np.ascontiguousarray(f.read(1).astype(np.float32))
+    return np.ascontiguousarray(_read_all(path)[0])
+
+
+def _read_all(path):
+    """-> float32 array (bands, h, w) without rasterio"""
     try:
         from PIL import Image
         with Image.open(path) as im:
@@ -29,18 +34,28 @@ def read_band(path):
         a = cv2.imread(path, cv2.IMREAD_UNCHANGED)
         if a is None:
             raise
-    if a.ndim == 3:
-        a = a[..., 0]
+        if a.ndim == 3:
+            a = a[..., ::-1]          # OpenCV stores BGR
+    a = a[None] if a.ndim == 2 else np.moveaxis(a, 2, 0)
     return np.ascontiguousarray(a.astype(np.float32))
 
 
-def read_window(path, x, y, w, h):
-    """-> float32 array of the w x h window at (x, y) of the first band."""
+def band_count(path):
+    if _HAVE_RASTERIO:
+        with rasterio.open(path, "r") as f:
+            return f.count
+    return _read_all(path).shape[0]
+
+
+def read_window(path, x, y, w, h, band=1):
+    """-> float32 array of the w x h window at (x, y) of band `band` (1-based, as in GDAL)."""
     if _HAVE_RASTERIO:
         from rasterio.windows import Window
         with rasterio.open(path, "r") as f:
-            return np.ascontiguousarray(f.read(1, window=Window(x, y, w, h)).astype(np.float32))
-    return np.ascontiguousarray(read_band(path)[y:y + h, x:x + w])
+            return np.ascontiguousarray(f.read(band, window=Window(x, y, w, h)).astype(np.float32))
+    if band == 1:
+        return np.ascontiguousarray(read_band(path)[y:y + h, x:x + w])
+    return np.ascontiguousarray(_read_all(path)[band - 1, y:y + h, x:x + w])
 
 
 def image_size(path):
@@ -48,9 +63,13 @@ def image_size(path):
     if _HAVE_RASTERIO:
         with rasterio.open(path, "r") as f:
             return f.width, f.height
-    from PIL import Image
-    with Image.open(path) as im:
-        return im.size
+    try:
+        from PIL import Image
+        with Image.open(path) as im:
+            return im.size
+    except Exception:            # e.g. a multi-band float TIFF, which Pillow does not decode
+        a = _read_all(path)
+        return a.shape[2], a.shape[1]
 
 
 def write_float_tiff(path, a):
@@ -62,6 +81,26 @@ def write_float_tiff(path, a):
         return
     from PIL import Image
     Image.fromarray(a, mode="F").save(path, format="TIFF")
+
+
+def write_float_tiff_bands(path, bands):
+    """float32 TIFF with one band per array of `bands` (what the reference's `homography` writes for a colour image,
+    3rdparty/homography/main.cpp: one RasterIO per band)."""
+    bands = [np.ascontiguousarray(b, dtype=np.float32) for b in bands]
+    if len(bands) == 1:
+        return write_float_tiff(path, bands[0])
+    if _HAVE_RASTERIO:
+        h, w = bands[0].shape
+        with rasterio.open(path, "w", driver="GTiff", height=h, width=w, count=len(bands), dtype="float32") as f:
+            for k, b in enumerate(bands):
+                f.write(b, k + 1)
+        return
+    import cv2
+    if len(bands) not in (3, 4):
+        raise ValueError("writing a %d-band float TIFF needs rasterio" % len(bands))
+    a = np.stack(bands[:3][::-1] + bands[3:], axis=2)      # OpenCV stores BGR(A)
+    if not cv2.imwrite(path, a):
+        raise IOError("cv2.imwrite failed for %s" % path)
 
 
 def write_mask_png(path, m):

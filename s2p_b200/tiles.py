@@ -19,6 +19,29 @@ def shard(n_items, rank, world):
     return list(range(start, start + base + (1 if rank < extra else 0)))
 
 
+class DynamicQueue:
+    """Dynamic sharding of a fixed list of n_items over the ranks: every rank pulls the next `chunk` indices from one
+    shared counter until the list is exhausted, so a slow rank takes fewer tiles and the tail is at most one chunk
+    (SURVEY.md section 8e).  The counter lives in the torch.distributed key-value store (one small round trip per
+    chunk, no collective on the data path); with world == 1 it is a local integer."""
+
+    def __init__(self, n_items, chunk, world=1, store=None, key="s2pb_tile_queue"):
+        self.n, self.chunk, self.world, self.store, self.key = int(n_items), int(chunk), world, store, key
+        self._local = 0
+        if world > 1 and store is None:
+            import torch.distributed as dist
+            self.store = dist.distributed_c10d._get_default_store()
+
+    def next(self):
+        """-> list of item indices (empty when the queue is drained)"""
+        if self.world == 1:
+            start = self._local
+            self._local += self.chunk
+        else:
+            start = self.store.add(self.key, self.chunk) - self.chunk
+        return list(range(min(start, self.n), min(start + self.chunk, self.n)))
+
+
 def checksum(a):
     """Order-independent-free 64-bit digest of a raster (NaN payloads normalised)."""
     b = np.ascontiguousarray(a)

@@ -31,12 +31,19 @@ def test_port_matches_reference_function(n):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,op", [(2, "average_if_close"), (3, "average_if_close"), (4, "np.nanmedian"), (3, "np.nanmean"),
-                                  (5, "np.nanmin"), (2, "np.nanmax")])
-def test_gpu_merge_matches_port(engine, n, op):
+                                  (5, "np.nanmin"), (2, "np.nanmax"), (3, "np.median"), (4, "np.mean"), (2, "np.min"), (3, "np.max"),
+                                  (9, "np.nanmean"), (13, "np.mean"), (16, "np.nanmean")])
+@pytest.mark.parametrize("sub_f32", [None, True, False])
+def test_gpu_merge_matches_port(engine, n, op, sub_f32):
+    """sub_f32: the offsets are subtracted in float32 (NumPy < 2) or float64 (NumPy >= 2); None = whatever the NumPy of
+    this environment does with the reference's own expression.  n >= 8 exercises NumPy's pairwise summation."""
     from oracle import fusion_oracle as F
     maps, offsets = _maps(n, seed=10 + n)
-    got = engine.merge_n(maps, offsets, op, threshold=3)
-    want = F.merge_port(maps, offsets, op, 3)
+    if op in ("np.mean", "np.median", "np.min", "np.max"):
+        for m in maps[1:]:
+            m[np.isnan(m) & (np.arange(m.shape[1])[None, :] % 3 > 0)] = 101.5     # leave pixels where no value is NaN
+    got = engine.merge_n(maps, offsets, op, threshold=3, sub_f32=sub_f32)
+    want = F.merge_port(maps, offsets, op, 3, sub_f32=sub_f32)
     assert same(got, want), "%d px differ" % int((~((got == want) | (np.isnan(got) & np.isnan(want)))).sum())
 
 

@@ -74,3 +74,20 @@ def test_dropin_file_contract(engine, oracle, tmp_path):
     assert np.abs(ref[both] - got[both]).max() <= REL_TOL * np.abs(src).max()
     with pytest.raises(subprocess.CalledProcessError):      # the binary exits with "empty roi"
         common.image_apply_homography(out, im, _rot(0, 1.0, 5000, 5000), 50, 50)
+
+
+def test_dropin_warps_every_band(engine, oracle, tmp_path):
+    """s2p/__init__.py:276 sends the multi-band colour image through image_apply_homography; the reference binary warps
+    every band (3rdparty/homography/main.cpp loops over GetRasterCount)."""
+    from s2p_b200 import common, rasterio_compat as rio
+    bands = [_src(200, 260, seed=10 + k, nan=False) for k in range(3)]
+    im, out = str(tmp_path / "clr.tif"), str(tmp_path / "clr_rect.tif")
+    rio.write_float_tiff_bands(im, bands)
+    H = _rot(-0.08, 1.0, 12, 9)
+    common.image_apply_homography(out, im, H, 180, 140)
+    assert rio.band_count(out) == 3
+    for k in range(3):
+        got = rio.read_window(out, 0, 0, 180, 140, k + 1)
+        one = engine.homography(bands[k], H, 180, 140)
+        assert np.array_equal(got, one, equal_nan=True)
+    assert not np.array_equal(rio.read_window(out, 0, 0, 180, 140, 1), rio.read_window(out, 0, 0, 180, 140, 2), equal_nan=True)

@@ -110,6 +110,26 @@ def test_raster_roundtrip(tmp_path):
     assert np.array_equal(rio.read_band(q).astype(np.uint8), m)
 
 
+def test_multiband_raster_roundtrip(tmp_path):
+    """the colour image of s2p/__init__.py:276 has several bands; band order survives the TIFF and PNG paths"""
+    from s2p_b200 import rasterio_compat as rio
+    rng = np.random.default_rng(0)
+    bands = [rng.uniform(0, 255, (20, 30)).astype(np.float32) for _ in range(3)]
+    bands[1][3, 4] = np.nan
+    p = str(tmp_path / "c.tif")
+    rio.write_float_tiff_bands(p, bands)
+    assert rio.band_count(p) == 3 and rio.image_size(p) == (30, 20)
+    for k in range(3):
+        assert np.array_equal(rio.read_window(p, 2, 3, 10, 8, k + 1), bands[k][3:11, 2:12], equal_nan=True)
+    assert np.array_equal(rio.read_band(p), bands[0])
+    from PIL import Image
+    rgb = rng.uniform(0, 255, (20, 30, 3)).astype(np.uint8)
+    q = str(tmp_path / "c.png")
+    Image.fromarray(rgb).save(q)
+    assert rio.band_count(q) == 3
+    assert np.array_equal(rio.read_window(q, 0, 0, 30, 20, 3), rgb[..., 2].astype(np.float32))
+
+
 def test_synth_is_deterministic_and_shaped():
     from s2p_b200.synth import make_pair
     a, b, d = make_pair(40, 60, -8, 7, seed=3, nan_border=0.1)
@@ -164,6 +184,40 @@ def test_gloo_two_ranks_shard_and_gather(tmp_path):
     out = subprocess.run(["python", "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
                           "127.0.0.1", "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert "GATHER_OK 6" in out.stdout, out.stdout + out.stderr
+
+
+def test_gloo_two_ranks_dynamic_queue(tmp_path):
+    """world_size 2 on CPU: the dynamic tile queue of bench.py's strong-scaling configuration (BASELINE configs[3]) hands
+    every tile to exactly one rank, also when one rank is slower."""
+    script = tmp_path / "q.py"
+    script.write_text(
+        "import os, sys, time\n"
+        "sys.path.insert(0, %r)\n"
+        "import numpy as np, torch, torch.distributed as dist\n"
+        "from s2p_b200.tiles import DynamicQueue\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "n = 37\n"
+        "q = DynamicQueue(n, 4, w)\n"
+        "mine = []\n"
+        "while True:\n"
+        "    ids = q.next()\n"
+        "    if not ids: break\n"
+        "    mine += ids\n"
+        "    time.sleep(0.02 if r == 0 else 0.002)\n"
+        "t = torch.zeros(n, dtype=torch.int64)\n"
+        "t[mine] = 1\n"
+        "dist.all_reduce(t)\n"
+        "assert bool((t == 1).all()), t\n"
+        "print('QUEUE_OK rank %%d took %%d' %% (r, len(mine)))\n"
+        "dist.destroy_process_group()\n" % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29618")
+    out = subprocess.run(["python", "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29618", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.stdout.count("QUEUE_OK") == 2, out.stdout + out.stderr
+    from s2p_b200.tiles import DynamicQueue
+    q = DynamicQueue(10, 4)
+    assert [q.next(), q.next(), q.next(), q.next()] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9], []]
 
 
 def test_public_header_is_plain_c(tmp_path):
