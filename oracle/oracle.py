@@ -249,6 +249,29 @@ def run_ref(im1, im2, dmin, dmax, params, threads=1, extra_env=None, workdir=Non
     return out
 
 
+def have_ref_mask():
+    return os.access(os.path.join(REF_DIR, "backflow"), os.X_OK) and os.access(os.path.join(REF_DIR, "plambda"), os.X_OK)
+
+
+def ref_rejection_mask(disp, im1, im2, workdir=None):
+    """create_rejection_mask (s2p/block_matching.py:18-32) with the reference's own programs (oracle/_ref/{plambda,backflow} =
+    c/plambda.c, c/backflow.c compiled in place), the same three commands, through PFM files.  -> uint8 0/1 mask."""
+    tmp = workdir or tempfile.mkdtemp(prefix="s2pb_mask_")
+    d, a, b = (os.path.join(tmp, n) for n in ("disp.pfm", "im1.pfm", "im2.pfm"))
+    t1, t2, m = (os.path.join(tmp, n) for n in ("tmp1.pfm", "tmp2.pfm", "mask.pfm"))
+    write_pfm(d, disp)
+    write_pfm(a, im1)
+    write_pfm(b, im2)
+    pl, bf = os.path.join(REF_DIR, "plambda"), os.path.join(REF_DIR, "backflow")
+    run = lambda argv: subprocess.run(argv, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    run([pl, d, "x 0 join", "-o", t1])
+    run([bf, t1, b, t2])
+    run([pl, d, a, t2, "x isfinite y isfinite z isfinite and and vmul", "-o", m])
+    out = read_pfm(m)
+    assert np.all((out == 0) | (out == 1))
+    return out.astype(np.uint8)
+
+
 def read_costvolume_dump(path):
     """DUMP_COSTVOLUME=1 format (mgm_costvolume.cc:222-234): int nx, ny, ndisp, dmin; floats."""
     with open(path, "rb") as f:

@@ -6,7 +6,7 @@ from s2p_b200.engine import Engine, default_params
 from s2p_b200.synth import make_pair
 
 h = w = int(os.environ.get("N", 1024)); dmin, dmax = -64, 63
-ref, sec, gt = make_pair(h, w, dmin, dmax, seed=0)
+ref, sec, gt = make_pair(h, w, dmin, dmax, seed=0, nan_border=float(os.environ.get("NANB", 0)))
 eng = Engine(0)
 p = default_params("mgm")
 for it in range(4):

@@ -290,3 +290,55 @@ def test_exact_zero_pixels_without_nodata(engine, oracle):
     out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm"), want_right=True)
     d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params())
     assert same(out["disp"], d) and same(out["conf"], c) and same(out["disp_right"], dr)
+
+
+@pytest.mark.parametrize("name", ["c2_plain", "c2_nodata"])
+def test_full_size_tile_matches_reference_binary(engine, name):
+    """BASELINE configs[1] at its full size: one 1024 x 1024 x 128 tile against the digests of the unmodified reference
+    binary's output (tests/golden/full_c2.json, generator tests/golden/make_golden_full.py), block of 32 rows by block."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_full import digests
+    from s2p_b200.engine import default_params
+    path = os.path.join(os.path.dirname(__file__), "golden", "full_c2.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/full_c2.json not generated")
+    g = json.load(open(path))[name]
+    ref, sec, _ = make_pair(g["h"], g["w"], g["dmin"], g["dmax"], seed=g["seed"], nan_border=g["nan_border"])
+    out = engine.mgm(ref, sec, g["dmin"], g["dmax"], default_params("mgm"), want_right=True)
+    for key, arr in (("disp", out["disp"]), ("conf", out["conf"]), ("dispR", out["disp_right"])):
+        got = digests(arr)
+        bad = [k for k, (a, b) in enumerate(zip(got, g[key])) if a != b]
+        assert not bad, "%s differs from the reference binary in %d of %d row blocks (first: rows %d..)" % (
+            key, len(bad), len(got), bad[0] * g["block_rows"])
+
+
+def test_eight_tiles_in_flight_equal_serial(engine):
+    """What bench.py times: >= 8 DISTINCT tiles through s2pb_mgm_batch with 8 workspaces in flight (the WTA of one tile
+    overlaps the aggregation of the next, copies overlap both), each compared with its own serial result."""
+    from s2p_b200.engine import default_params
+    h, w, dmin, dmax = 200, 320, -40, 39
+    pairs = [make_pair(h, w, dmin, dmax, seed=300 + k, nan_border=0.04 if k % 3 == 1 else 0.0)[:2] for k in range(11)]
+    p = default_params("mgm")
+    serial = [engine.mgm(a, b, dmin, dmax, p) for a, b in pairs]
+    engine.reserve(8, w, h, dmax - dmin + 2)
+    for _ in range(2):          # the second pass reuses warm workspaces
+        disp, conf, mask = engine.mgm_batch([a for a, _ in pairs], [b for _, b in pairs], dmin, dmax, p)
+        for k, one in enumerate(serial):
+            assert same(disp[k], one["disp"]), "tile %d: %d px differ" % (k, nmismatch(disp[k], one["disp"]))
+            assert same(conf[k], one["conf"]) and np.array_equal(mask[k], one["mask"])
+
+
+def test_rejection_mask_matches_reference_programs(engine, oracle):
+    """the mask kernel against the reference's own plambda / backflow / plambda chain (oracle/_ref, c/*.c compiled in place)"""
+    if not oracle.have_ref_mask():
+        pytest.skip("oracle/_ref/backflow not built")
+    rng = np.random.default_rng(4)
+    for seed, (h, w, dmin, dmax) in enumerate([(70, 110, -12, 12), (45, 200, -30, 8)]):
+        ref, sec, gt = make_pair(h, w, dmin, dmax, seed=50 + seed, nan_border=0.06)
+        d = gt + rng.uniform(-0.7, 0.7, gt.shape).astype(np.float32)
+        d[rng.random(d.shape) < 0.1] = np.nan
+        d[:, :3] -= 7.3
+        assert np.array_equal(engine.rejection_mask(d, ref, sec), oracle.ref_rejection_mask(d, ref, sec))

@@ -207,3 +207,21 @@ def test_fuzz_sample_against_reference_binary(oracle):
                        timeout=280)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "done: 24 cases, 0 with a mismatch" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("shape,dmin,dmax,seed", [((60, 100), -11, 12, 0), ((90, 140), -20, 20, 1), ((41, 77), -5, 30, 2), ((33, 50), 0, 9, 3)])
+def test_rejection_mask_port_matches_reference_programs(oracle, shape, dmin, dmax, seed):
+    """create_rejection_mask (s2p/block_matching.py:18-32): the port against the reference's own plambda / backflow / plambda
+    chain (c/plambda.c, c/backflow.c + bicubic.c + getpixel.c compiled in place as oracle/_ref/{plambda,backflow}), on tiles
+    with no-data in both images, NaN disparities and disparities pointing outside the image."""
+    if not oracle.have_ref_mask():
+        pytest.skip("oracle/_ref/backflow not built (needs /root/reference)")
+    from s2p_b200.synth import make_pair
+    h, w = shape
+    rng = np.random.default_rng(seed)
+    ref, sec, gt = make_pair(h, w, dmin, dmax, seed=seed, nan_border=0.08)
+    d = gt + rng.uniform(-0.7, 0.7, gt.shape).astype(np.float32)
+    d[rng.random(d.shape) < 0.1] = np.nan
+    d[:, :3] -= 7.3                   # backflow samples outside the image (getsample_0: zero outside)
+    d[:, -3:] += 6.6
+    assert np.array_equal(oracle.port.rejection_mask(d, ref, sec), oracle.ref_rejection_mask(d, ref, sec))
