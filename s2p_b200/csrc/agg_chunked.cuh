@@ -28,18 +28,23 @@
 
 namespace s2pb {
 
-constexpr int kCkWarps = 16;       // scanlines per band = warps per CTA
+constexpr int kCkWarps = 16;       // scanlines per band = warps per CTA for slabs of up to 512 slots; wider slabs run with
+                                   // 8 (<= 1024 slots) or 4 (<= 2048) warps so that the rings still fit shared memory
 constexpr int kCkThreads = kCkWarps * 32;
 constexpr int kCkRing = 4;         // ring slots per scanline (a reader is at most 3 pixels behind the writer)
-constexpr int kCkStage = 4;        // cp.async pipeline depth in pixel steps
-constexpr int kCkR0 = 8;           // slots of the previous band's scanline
+constexpr int kCkStage = 4;        // cp.async pipeline depth in pixel steps (2 for the slabs wider than 512 slots)
 constexpr int kCkPad = 4;          // floats of +INF guard before and after a stored vector (keeps 16-byte alignment)
+// slots of the previous band's scanline for a pipeline depth of `stage` (> stage + 1: pixel 0 is staged ahead)
+__host__ __device__ constexpr int ck_r0(int stage) { return 2 * stage; }
+// warps per CTA (= scanlines per band) and pipeline depth for a slab of DP slots
+__host__ __device__ inline int ck_warps(int DP) { return DP <= 512 ? 16 : DP <= 1024 ? 8 : 4; }
+__host__ __device__ inline int ck_stage(int DP) { return DP <= 512 ? 4 : 2; }
 
 struct ChunkedParams {
     AggParams A;
     const short *lo[kMaxPV], *hi[kMaxPV];   // per pass-view: the view's per-pixel label range
     int gmin[kMaxPV];                       // ... and the label of slot 0
-    int DP;                                 // slots per pixel (multiple of 32, <= 512)
+    int DP;                                 // slots per pixel (multiple of 32, <= 2048)
     int fill_inf;                           // 1: write +INF to the chunks a pixel skips (the dense WTA kernel then works on the
                                             // result); 0: leave them untouched (the chunk-skipping WTA never reads them)
 };
@@ -48,20 +53,21 @@ struct ChunkedParams {
 struct CkSmem {
     int DP, vstride;                        // vstride = DP + 2 * kCkPad floats per stored vector
     size_t ring_off, meta_off, r0_off, r0m_off, cst_off, rng_off, r0rng_off, bytes;
-    __host__ __device__ explicit CkSmem(int dp) : DP(dp), vstride(dp + 2 * kCkPad)
+    __host__ __device__ CkSmem(int dp, int warps, int stage) : DP(dp), vstride(dp + 2 * kCkPad)
     {
+        const int r0n = ck_r0(stage);
         ring_off = 0;                                                               // float [warps][ring][vstride]
-        meta_off = ring_off + sizeof(float) * kCkWarps * kCkRing * vstride;         // float min, int ea, int eb per slot
-        r0_off = meta_off + 12 * kCkWarps * kCkRing;                                // float [kCkR0][vstride]
-        r0m_off = r0_off + sizeof(float) * kCkR0 * vstride;                         // float [kCkR0]
-        cst_off = (r0m_off + sizeof(float) * kCkR0 + 15) / 16 * 16;                 // half [warps][stage][DP]
-        rng_off = cst_off + sizeof(__half) * kCkWarps * kCkStage * dp;              // 2 words per (warp, stage): lo, hi
-        r0rng_off = rng_off + 8 * kCkWarps * kCkStage;                              // 2 words per previous-band slot
-        bytes = r0rng_off + 8 * kCkR0;
+        meta_off = ring_off + sizeof(float) * warps * kCkRing * vstride;            // float min, int ea, int eb per slot
+        r0_off = meta_off + 12 * warps * kCkRing;                                   // float [r0n][vstride]
+        r0m_off = r0_off + sizeof(float) * r0n * vstride;                           // float [r0n]
+        cst_off = (r0m_off + sizeof(float) * r0n + 15) / 16 * 16;                   // half [warps][stage][DP]
+        rng_off = cst_off + sizeof(__half) * warps * stage * dp;                    // 2 words per (warp, stage): lo, hi
+        r0rng_off = rng_off + 8 * warps * stage;                                    // 2 words per previous-band slot
+        bytes = r0rng_off + 8 * r0n;
     }
 };
 
-template <int TSGM, int TYPE, bool SCALED>
+template <int TSGM, int TYPE, bool SCALED, int STAGE>
 __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short *__restrict__ lo_img, const short *__restrict__ hi_img,
                                                  int gmin, int DP, bool fill_inf, int band, float P1, float P2,
                                                  const float *__restrict__ lut, const int *abort_flag, unsigned char *smem)
@@ -73,8 +79,10 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
     constexpr bool usePrev = useCn || useB || useE;
     constexpr int SKEW = useE ? 2 : 1;
     constexpr int LEAD = useE ? 1 : 0;
+    constexpr int kCkStage = STAGE, kCkR0 = ck_r0(STAGE);    // (shadow the defaults: this instantiation's pipeline depth)
     constexpr int S = kCkStage - 1;
-    const CkSmem SM(DP);
+    const int kCkWarps = (int)(blockDim.x >> 5);             // scanlines per band
+    const CkSmem SM(DP, kCkWarps, STAGE);
     const int NC = DP >> 5, VS = SM.vstride;
     const int nI = pd.nI;
     const int nsteps = nI + (kCkWarps - 1) * SKEW;
@@ -297,11 +305,12 @@ __device__ __forceinline__ void run_band_chunked(const PassDesc &pd, const short
     cp_async_wait<0>();
 }
 
-template <int TSGM, bool SCALED>
+template <int TSGM, bool SCALED, int STAGE>
 __global__ void __launch_bounds__(kCkThreads) aggregate_chunked_kernel(const __grid_constant__ ChunkedParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_item;
+    const int kCkWarps = (int)(blockDim.x >> 5);
     // bands of kCkWarps scanlines here (the dense kernel's bands hold kNW): recompute the counts
     int maxBands = 0;
     for (int v = 0; v < P.A.nPV; v++) { const int nb = (P.A.pv[v].nS + kCkWarps - 1) / kCkWarps; if (nb > maxBands) maxBands = nb; }
@@ -315,8 +324,8 @@ __global__ void __launch_bounds__(kCkThreads) aggregate_chunked_kernel(const __g
         const int band = item / P.A.nPV, pvi = item - band * P.A.nPV;
         const PassDesc &pd = P.A.pv[pvi];
         if (band >= (pd.nS + kCkWarps - 1) / kCkWarps) continue;
-        if (pd.type == 0) run_band_chunked<TSGM, 0, SCALED>(pd, P.lo[pvi], P.hi[pvi], P.gmin[pvi], P.DP, P.fill_inf != 0, band, P.A.P1, P.A.P2, P.A.lut, P.A.abort_flag, smem);
-        else run_band_chunked<TSGM, 1, SCALED>(pd, P.lo[pvi], P.hi[pvi], P.gmin[pvi], P.DP, P.fill_inf != 0, band, P.A.P1, P.A.P2, P.A.lut, P.A.abort_flag, smem);
+        if (pd.type == 0) run_band_chunked<TSGM, 0, SCALED, STAGE>(pd, P.lo[pvi], P.hi[pvi], P.gmin[pvi], P.DP, P.fill_inf != 0, band, P.A.P1, P.A.P2, P.A.lut, P.A.abort_flag, smem);
+        else run_band_chunked<TSGM, 1, SCALED, STAGE>(pd, P.lo[pvi], P.hi[pvi], P.gmin[pvi], P.DP, P.fill_inf != 0, band, P.A.P1, P.A.P2, P.A.lut, P.A.abort_flag, smem);
     }
 }
 

@@ -63,7 +63,9 @@ __global__ void rt_flag_kernel(const float *__restrict__ img, int w, int h, floa
 
 // Y[r][o] = (sum_{i=0}^{n-1} T[o][i] * X[r][i]) * scale-by-division, r over the listed rows (or all rows when
 // rowlist == nullptr).  The sum runs in ascending i with separately rounded multiply and add, from 0.0, like a plain C
-// loop compiled without contraction.  T is [n][n] row-major.  64 outputs x 64 rows per block, 4 x 4 per thread.
+// loop compiled without contraction.  T is [n][n] row-major.  64 outputs x 32 rows per block, 4 x 2 per thread (the FP64
+// pipe issues one warp instruction every two cycles, so a small register tile already keeps it busy; the smaller tile
+// gives 512 work items on a 1024 x 1024 image for the 148 SMs).
 // IN = float (image rows) or double.  DIVN: divide the sum by n (the forward transform's normalisation, shear.c:62-63).
 // `mul` (optional, [n]): the output is multiplied by mul[o] (the phase factor cos(o a));
 // `mul2`/`Y2` (optional): a second output Y2[r][o-1] = y * mul2[o] for o >= 1 and Y2[r][n-1] = 0 (the antisymmetric
@@ -74,57 +76,62 @@ __global__ void __launch_bounds__(256) dct_gemm_kernel(const double *__restrict_
                                                        double *__restrict__ Y, const double *__restrict__ mul,
                                                        const double *__restrict__ mul2, double *__restrict__ Y2)
 {
-    constexpr int TO = 64, TR = 64, TK = 16;
+    constexpr int TO = 64, TR = 32, TK = 16, QA = 4, QB = 2;
     __shared__ double Ts[TK][TO + 2];
     __shared__ double Xs[TK][TR + 2];
+    __shared__ int rows_s[TR];
     const int nrows = rowlist ? st->nrows : nrows_all;
     const int otiles = (n + TO - 1) / TO, rtiles = (nrows + TR - 1) / TR;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     for (int item = blockIdx.x; item < otiles * rtiles; item += gridDim.x) {
         const int o0 = (item % otiles) * TO, r0 = (item / otiles) * TR;
-        double acc[4][4];
+        __syncthreads();
+        if (threadIdx.x < TR) {
+            const int rr = r0 + threadIdx.x;
+            rows_s[threadIdx.x] = rr < nrows ? (rowlist ? rowlist[rr] : rr) : -1;
+        }
+        double acc[QA][QB];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+        for (int a = 0; a < QA; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+            for (int b = 0; b < QB; b++) acc[a][b] = 0.0;
         for (int k0 = 0; k0 < n; k0 += TK) {
             __syncthreads();
-            // T tile: 64 outputs x 16 inputs; thread t loads output (t >> 2), inputs 4 (t & 3) .. +3
-            {
+            {   // T tile: 64 outputs x 16 inputs; thread t loads output (t >> 2), inputs 4 (t & 3) .. +3
                 const int o = o0 + (threadIdx.x >> 2), kk = 4 * (threadIdx.x & 3);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const int k = k0 + kk + q;
                     Ts[kk + q][threadIdx.x >> 2] = (o < n && k < n) ? T[(size_t)o * n + k] : 0.0;
                 }
-                const int rr = r0 + (threadIdx.x >> 2);
-                int row = -1;
-                if (rr < nrows) row = rowlist ? rowlist[rr] : rr;
+                // X tile: 32 rows x 16 inputs; thread t loads row (t >> 3), inputs 2 (t & 7), + 1
+                const int row = rows_s[threadIdx.x >> 3], kx = 2 * (threadIdx.x & 7);
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int k = k0 + kk + q;
-                    Xs[kk + q][threadIdx.x >> 2] = (row >= 0 && k < n) ? (double)X[(size_t)row * n + k] : 0.0;
+                for (int q = 0; q < 2; q++) {
+                    const int k = k0 + kx + q;
+                    Xs[kx + q][threadIdx.x >> 3] = (row >= 0 && k < n) ? (double)X[(size_t)row * n + k] : 0.0;
                 }
             }
             __syncthreads();
             const int kmax = (n - k0 < TK) ? n - k0 : TK;
             for (int kk = 0; kk < kmax; kk++) {
-                double a[4], b[4];
+                double a[QA], b[QB];
 #pragma unroll
-                for (int q = 0; q < 4; q++) { a[q] = Ts[kk][tx + 16 * q]; b[q] = Xs[kk][ty + 16 * q]; }
+                for (int q = 0; q < QA; q++) a[q] = Ts[kk][tx + 16 * q];
 #pragma unroll
-                for (int qa = 0; qa < 4; qa++)
+                for (int q = 0; q < QB; q++) b[q] = Xs[kk][ty + 16 * q];
 #pragma unroll
-                    for (int qb = 0; qb < 4; qb++) acc[qa][qb] = __dadd_rn(acc[qa][qb], __dmul_rn(a[qa], b[qb]));
+                for (int qa = 0; qa < QA; qa++)
+#pragma unroll
+                    for (int qb = 0; qb < QB; qb++) acc[qa][qb] = __dadd_rn(acc[qa][qb], __dmul_rn(a[qa], b[qb]));
             }
         }
 #pragma unroll
-        for (int qb = 0; qb < 4; qb++) {
-            const int rr = r0 + ty + 16 * qb;
-            if (rr >= nrows) continue;
-            const int row = rowlist ? rowlist[rr] : rr;
+        for (int qb = 0; qb < QB; qb++) {
+            const int row = rows_s[ty + 16 * qb];
+            if (row < 0) continue;
 #pragma unroll
-            for (int qa = 0; qa < 4; qa++) {
+            for (int qa = 0; qa < QA; qa++) {
                 const int o = o0 + tx + 16 * qa;
                 if (o >= n) continue;
                 double y = acc[qa][qb];
@@ -140,29 +147,43 @@ __global__ void __launch_bounds__(256) dct_gemm_kernel(const double *__restrict_
 }
 
 // q = 0: out[r][i] = (float)(0.5 * (sum_k T01[i][k] Y[r][k] + 0.0)) for the flagged pixels of the listed rows (the
-// antisymmetric part is identically +0: its inputs are Y[k] sin(0) = +-0).  T01t is the TRANSPOSED table [k][i] so that
-// the threads of a warp (consecutive i) read consecutive addresses.  One block per listed row.
+// antisymmetric part is identically +0: its inputs are Y[k] sin(0) = +-0).  T01t is the TRANSPOSED table [k][i].  One block
+// per listed row (the grid covers every image row; blocks beyond the list return): the row's flagged pixels are
+// compacted into a list first, so that the few of them -- a no-data margin is a few percent of a row -- share one pass, and
+// each thread then runs its pixel's sequential sum with 16 table loads in flight.
 __global__ void __launch_bounds__(256) rt_inverse_kernel(const double *__restrict__ T01t, const double *__restrict__ Y, int n,
                                                          const RtState *st, const int *__restrict__ rowlist,
                                                          const float *__restrict__ rowthr, const float *__restrict__ img, float *__restrict__ rt)
 {
-    extern __shared__ double ys[];     // [n]
+    extern __shared__ double ys[];     // [n] doubles, then the list of flagged columns [n] ints
+    int *list = reinterpret_cast<int *>(ys + n);
+    __shared__ int count;
     const int nrows = st->nrows;
     for (int rr = blockIdx.x; rr < nrows; rr += gridDim.x) {
         const int row = rowlist[rr];
         const float thr = rowthr[row];
         __syncthreads();
-        for (int k = threadIdx.x; k < n; k += blockDim.x) ys[k] = Y[(size_t)row * n + k];
+        if (threadIdx.x == 0) count = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-            const int i = i0 + threadIdx.x;
-            const bool flagged = i < n && fabsf(img[(size_t)row * n + i]) <= thr;
-            if (!__any_sync(0xffffffffu, flagged)) continue;
-            if (!flagged) continue;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            ys[k] = Y[(size_t)row * n + k];
+            if (fabsf(img[(size_t)row * n + k]) <= thr) list[atomicAdd(&count, 1)] = k;
+        }
+        __syncthreads();
+        const int m = count;
+        for (int q = threadIdx.x; q < m; q += blockDim.x) {
+            const int i = list[q];
             double acc = 0.0;
             const double *t = T01t + i;
-#pragma unroll 8
-            for (int k = 0; k < n; k++) acc = __dadd_rn(acc, __dmul_rn(t[(size_t)k * n], ys[k]));
+            int k = 0;
+            for (; k + 16 <= n; k += 16) {
+                double c[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) c[u] = __ldg(t + (size_t)(k + u) * n);
+#pragma unroll
+                for (int u = 0; u < 16; u++) acc = __dadd_rn(acc, __dmul_rn(c[u], ys[k + u]));
+            }
+            for (; k < n; k++) acc = __dadd_rn(acc, __dmul_rn(__ldg(t + (size_t)k * n), ys[k]));
             rt[(size_t)row * n + i] = (float)__dmul_rn(0.5, __dadd_rn(acc, 0.0));
         }
     }

@@ -131,46 +131,68 @@ __global__ void cc_init_kernel(const float *__restrict__ in, int n, int *__restr
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { lab[i] = isnan(in[i]) ? -1 : i; area[i] = 0; }
 }
-// horizontal links: one thread per row walks it left to right and labels every run of linked pixels with the
-// index of the run's first pixel -- no atomics.  (The reference makes no horizontal link in the last row.)
+// horizontal links: one warp per row.  A valid pixel whose left neighbour is invalid or not close starts a run; every
+// pixel of a run is labelled with the run's first pixel, found by a running maximum of the start indices (an inclusive
+// warp scan per 32-pixel chunk plus a carry) -- no atomics.  (The reference makes no horizontal link in the last row.)
 __global__ void cc_rows_kernel(const float *__restrict__ in, int w, int h, float thr, int *lab)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= h - 1) return;
     const float *row = in + (size_t)j * w;
     int *l = lab + (size_t)j * w;
-    int start = -1;
-    float prev = 0.f;
-    for (int i = 0; i < w; i++) {
-        const float a = row[i];
-        if (isnan(a)) { start = -1; continue; }              // lab stays -1 (cc_init)
-        // link (i-1, i) exists when i-1 < w-1 (always), both valid and close
-        if (start >= 0 && fabs((double)(prev - a)) < (double)thr) l[i] = j * w + start;
-        else { start = i; }
-        prev = a;
+    int carry = -1;
+    for (int i0 = 0; i0 < w; i0 += 32) {
+        const int i = i0 + lane;
+        const float a = i < w ? row[i] : __int_as_float(0x7fc00000);
+        const bool valid = !isnan(a);
+        float left = __shfl_up_sync(0xffffffffu, a, 1);
+        if (lane == 0) left = i0 > 0 ? row[i0 - 1] : __int_as_float(0x7fc00000);
+        const bool linked = valid && !isnan(left) && fabs((double)(left - a)) < (double)thr;
+        int s = (valid && !linked) ? i : -1;                   // index of the run start at or before me, within the chunk
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d && o > s) s = o; }
+        if (carry > s) s = carry;
+        if (valid && i < w) l[i] = j * w + s;                  // a valid pixel always has a start at or before it
+        carry = __shfl_sync(0xffffffffu, s, 31);
     }
 }
-// vertical links (none in the last column, as in the reference): union of the two runs' roots
+// vertical links (none in the last column, as in the reference): union of the two runs' roots.  When the column to the
+// left carries the same vertical link and both pixels continue their left neighbours' runs, the union is implied.
 __global__ void cc_link_kernel(const float *__restrict__ in, int w, int h, float thr, int *lab)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= w - 1 || j >= h - 1) return;
-    int p0 = j * w + i, p2 = p0 + w;
-    if (lab[p0] < 0 || lab[p2] < 0) return;
-    if (fabs((double)(in[p0] - in[p2])) < (double)thr) uf_union(lab, p0, p2);
+    const int p0 = j * w + i, p2 = p0 + w;
+    const float a = in[p0], b = in[p2];
+    if (isnan(a) || isnan(b)) return;
+    if (!(fabs((double)(a - b)) < (double)thr)) return;
+    if (i > 0 && j + 1 < h - 1) {                              // row j+1 has horizontal links only if it is not the last row
+        const float al = in[p0 - 1], bl = in[p2 - 1];
+        if (!isnan(al) && !isnan(bl) && fabs((double)(al - bl)) < (double)thr &&
+            fabs((double)(al - a)) < (double)thr && fabs((double)(bl - b)) < (double)thr) return;
+    }
+    uf_union(lab, p0, p2);
 }
-__global__ void cc_area_kernel(int n, int *lab, int *area)
+// every pixel points straight at its root (no unions run concurrently with this pass)
+__global__ void cc_flatten_kernel(int n, int *lab)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && lab[i] >= 0) atomicAdd(area + uf_find(lab, i), 1);
+    if (i < n && lab[i] >= 0) lab[i] = uf_find(lab, i);
+}
+// component areas: one atomic per distinct root and warp (a big component would otherwise serialise on one counter)
+__global__ void cc_area_kernel(int n, const int *__restrict__ lab, int *area)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const int r = i < n ? lab[i] : -1;                         // flattened: the root itself
+    const unsigned same = __match_any_sync(0xffffffffu, r);
+    if (r >= 0 && lane == __ffs(same) - 1) atomicAdd(area + r, __popc(same));
 }
 __global__ void cc_filter_kernel(const float *__restrict__ in, int n, const int *__restrict__ lab, const int *__restrict__ area,
                                  int minarea, float *__restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int r = lab[i];
-    if (r >= 0) r = uf_find(lab, i);
+    const int r = lab[i];                                      // flattened by cc_flatten_kernel
     out[i] = (r >= 0 && area[r] <= minarea) ? __int_as_float(0x7fc00000) : in[i];
 }
 

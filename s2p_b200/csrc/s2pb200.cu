@@ -425,6 +425,10 @@ static int plan_labels(int dmin, int dmax, bool sec_has_nodata, int gminv[2], in
     for (int vi = 0; vi < 2; vi++) { int d = gmaxv[vi] - gminv[vi] + 1; if (d > D) D = d; }
     return lpl_for(D);
 }
+// labels per lane of ONE view's slab.  The views may differ: a no-data pixel in the secondary image widens only the right
+// view's hull (by one label when |dmin| > dmax), and each view's kernels run at that view's own width -- the volumes are
+// [H][W][32 LPL_view] inside buffers sized for the wider view.
+static int view_lpl(const int gminv[2], const int gmaxv[2], int vi) { return lpl_for(gmaxv[vi] - gminv[vi] + 1); }
 
 static void fill_pass(PassDesc &pd, int pass, int w, int h)
 {
@@ -450,20 +454,24 @@ static int chunked_mode() { static int v = -1; if (v < 0) { const char *e = gete
 // slabs narrower than S2PB_CHUNKED_MIN_DP slots (default 160) stay with the dense kernels: on the coarse levels most
 // pixels use most of their chunks (scripts/range_width_analysis.py)
 static int chunked_min_dp() { static int v = -1; if (v < 0) { const char *e = getenv("S2PB_CHUNKED_MIN_DP"); v = e ? atoi(e) : 160; } return v; }
-static bool chunked_enabled(int DP) { return (chunked_mode() == 1 || chunked_mode() == 2) && DP >= chunked_min_dp(); }
-static bool chunked_wta_enabled(int DP) { return (chunked_mode() == 1 || chunked_mode() == 3) && DP >= chunked_min_dp(); }
+// Slabs wider than 512 slots (a level of mgm_multi whose label hull exceeds what the register-resident kernels hold) always take
+// the chunk-skipping kernels, which run with any width up to 2048 slots: the reference has no such limit
+// (mgm_costvolume.cc:63-72 allocates one vector per pixel of its own length).
+static bool chunked_enabled(int DP) { return DP > 512 || ((chunked_mode() == 1 || chunked_mode() == 2) && DP >= chunked_min_dp()); }
+static bool chunked_wta_enabled(int DP) { return DP > 512 || ((chunked_mode() == 1 || chunked_mode() == 3) && DP >= chunked_min_dp()); }
+static bool chunked_cost_enabled(int DP) { return DP > 512 || (chunked_mode() == 1 && DP >= chunked_min_dp()); }
 
 // general: the float-cost flavour; wgt[vi] = that view's weight image or nullptr (general only)
 // gminv: label of slot 0 per view (only needed by the chunk-skipping kernel; nullptr = dense kernel)
 static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, int LPL, float P1, float P2, int ndir, int tsgm,
                             const float *lut, cudaStream_t st, bool general = false, const float *const *wgt = nullptr,
-                            const int *gminv = nullptr)
+                            const int *gminv = nullptr, int first_view = 0)
 {
     AggParams P;
     memset(&P, 0, sizeof P);
     int mb = max_bands(w, h);
     P.nPV = 0; P.maxBands = 0;
-    for (int vi = 0; vi < nviews; vi++) {
+    for (int vi = first_view; vi < first_view + nviews; vi++) {
         CK(cudaMemsetAsync(s.v[vi].progress, 0, (size_t)kMaxPasses * mb * 4, st));
         for (int p = 0; p < ndir; p++) {
             PassDesc &pd = P.pv[P.nPV++];
@@ -484,7 +492,7 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
         Q.DP = 32 * LPL;
         Q.fill_inf = chunked_wta_enabled(32 * LPL) ? 0 : 1;   // the dense WTA reads every chunk
         int q = 0;
-        for (int vi = 0; vi < nviews; vi++)
+        for (int vi = first_view; vi < first_view + nviews; vi++)
             for (int p = 0; p < ndir; p++, q++) { Q.lo[q] = s.v[vi].lo; Q.hi[q] = s.v[vi].hi; Q.gmin[q] = gminv[vi]; }
         static bool configured = false;
         if (!configured) { if (agg_chunked_configure() != 0) return fail(S2PB_ERR_CUDA, "chunked aggregation: cudaFuncSetAttribute failed"); configured = true; }
@@ -551,7 +559,7 @@ static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t s
     if (ragged && !general && P.S == nullptr && chunked_wta_enabled(32 * LPL)) {  // experimental, mgm_multi levels only
         const int DP = 32 * LPL;
         static bool configured = false;
-        if (!configured) { CK(cudaFuncSetAttribute(wta_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 512 * 4)); configured = true; }
+        if (!configured) { CK(cudaFuncSetAttribute(wta_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 4)); configured = true; }
         wta_chunked_kernel<<<ctx->sm_count * 16, kWtaThreads, (size_t)(kWtaThreads / 32) * DP * sizeof(float), st>>>(P, DP);
         CK(cudaGetLastError());
         ctx->launches++;
@@ -639,11 +647,11 @@ static int round_trip_zero(s2pb_ctx *ctx, const float *img, int w, int h, float 
     int rc = dct_tables(ctx, w, false, &t);
     if (rc != S2PB_OK) return rc;
     static bool configured = false;
-    if (!configured) { CK(cudaFuncSetAttribute(rt_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8)); configured = true; }
+    if (!configured) { CK(cudaFuncSetAttribute(rt_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12)); configured = true; }
     CK(cudaMemsetAsync(state, 0, sizeof(RtState), st));
     rt_flag_kernel<<<h, 256, 0, st>>>(img, w, h, rt, state, rowlist, rowthr);
-    dct_gemm_kernel<float, true><<<ctx->sm_count * 3, 256, 0, st>>>(t->T10, img, w, h, state, rowlist, Y, nullptr, nullptr, nullptr);
-    rt_inverse_kernel<<<ctx->sm_count * 4, 256, (size_t)w * sizeof(double), st>>>(t->T01t, Y, w, state, rowlist, rowthr, img, rt);
+    dct_gemm_kernel<float, true><<<ctx->sm_count * 4, 256, 0, st>>>(t->T10, img, w, h, state, rowlist, Y, nullptr, nullptr, nullptr);
+    rt_inverse_kernel<<<h, 256, (size_t)w * 12, st>>>(t->T01t, Y, w, state, rowlist, rowthr, img, rt);
     ctx->launches += 3;
     CK(cudaGetLastError());
     return S2PB_OK;
@@ -657,7 +665,7 @@ static int shift_half(s2pb_ctx *ctx, const float *img, int w, int h, float *out,
     if (rc != S2PB_OK) return rc;
     const size_t npix = (size_t)w * h;
     double *ck = scratch, *sk = scratch + npix, *sym = scratch + 2 * npix, *anti = scratch + 3 * npix;
-    const int g = ctx->sm_count * 3;
+    const int g = ctx->sm_count * 4;
     dct_gemm_kernel<float, true><<<g, 256, 0, st>>>(t->T10, img, w, h, nullptr, nullptr, ck, t->mc, t->ms, sk);
     dct_gemm_kernel<double, false><<<g, 256, 0, st>>>(t->T01, ck, w, h, nullptr, nullptr, sym, nullptr, nullptr, nullptr);
     dct_gemm_kernel<double, false><<<g, 256, 0, st>>>(t->TR01, sk, w, h, nullptr, nullptr, anti, nullptr, nullptr, nullptr);
@@ -715,11 +723,12 @@ static int launch_remove_small_cc(s2pb_ctx *ctx, const float *in, float *out, in
     int n = w * h;
     dim3 b2(32, 8);
     cc_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(in, n, lab, area);
-    cc_rows_kernel<<<(h + 63) / 64, 64, 0, st>>>(in, w, h, 5.f, lab);
+    cc_rows_kernel<<<(h + 3) / 4, 128, 0, st>>>(in, w, h, 5.f, lab);                 // one warp per row
     cc_link_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(in, w, h, 5.f, lab);
+    cc_flatten_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, lab);
     cc_area_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, lab, area);
     cc_filter_kernel<<<(n + 255) / 256, 256, 0, st>>>(in, n, lab, area, minarea, out);
-    ctx->launches += 5;
+    ctx->launches += 6;
     CK(cudaGetLastError());
     return S2PB_OK;
 }
@@ -776,7 +785,12 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
         int d = gmaxv[vi] - gminv[vi] + 1; if (d > D) D = d;
     }
     int LPL = lpl_for(D);
-    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "a %dx%d level needs %d labels in its dense volume; 512 are supported", w, h, D);
+    if (LPL < 0) {      // hull wider than 512 labels: slab of ceil(D / 32) chunks through the chunk-skipping kernels (census costs only)
+        LPL = (D + 31) / 32;
+        if (general || LPL > 64)
+            return fail(S2PB_ERR_UNSUPPORTED, "a %dx%d level needs %d labels in its volume; %s", w, h, D,
+                        general ? "512 are supported for the float-cost flavour" : "2048 are supported");
+    }
     rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir, general ? 4 : 2);
     if (rc != S2PB_OK) return rc;
     TRACE(st, "level %dx%d zoom %d: hull L [%d,%d] R [%d,%d] -> LPL %d%s", w, h, zoom, gminv[0], gmaxv[0], gminv[1], gmaxv[1], LPL,
@@ -824,7 +838,7 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
             G.w = w; G.h = h; G.gmin = gminv[vi]; G.cost = p->cost; G.win = p->census_win; G.zoom = zoom;
             G.C = (float *)s.v[vi].C;
             rc = launch_cost_gen(ctx, LPL, G, st);
-        } else if (chunked_mode() == 1 && chunked_enabled(32 * LPL)) {      // experimental: only the chunks of each pixel's span
+        } else if (chunked_cost_enabled(32 * LPL)) {      // only the chunks of each pixel's span
             if (zoom == 2) cost_chunked_kernel<true><<<ctx->sm_count * 8, 256, 0, st>>>(s.v[vi].census, cen_rt[1 - vi], cen_half[1 - vi], w, h,
                                                                                   lo[vi], hi[vi], gminv[vi], 32 * LPL, (__half *)s.v[vi].C);
             else cost_chunked_kernel<false><<<ctx->sm_count * 8, 256, 0, st>>>(s.v[vi].census, cen_rt[1 - vi], nullptr, w, h,
@@ -1024,8 +1038,18 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
         nodata_hint = *(volatile int *)ctx->scratch_flag ? 3 : 0;
     }
     int gminv[2], gmaxv[2];
-    int LPL = plan_labels(dmin, dmax, (nodata_hint & 2) != 0, gminv, gmaxv);
-    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "disparity range [%d,%d] needs more than the 512 labels supported", dmin, dmax);
+    plan_labels(dmin, dmax, (nodata_hint & 2) != 0, gminv, gmaxv);
+    int LPLv[2] = {view_lpl(gminv, gmaxv, 0), view_lpl(gminv, gmaxv, 1)};
+    bool wide[2] = {false, false};
+    for (int vi = 0; vi < 2; vi++)
+        if (LPLv[vi] < 0) {      // more than 512 labels: chunk-skipping kernels on a slab of ceil(D / 32) chunks (census costs only)
+            LPLv[vi] = (gmaxv[vi] - gminv[vi] + 32) / 32;
+            wide[vi] = true;
+            if (general || LPLv[vi] > 64)
+                return fail(S2PB_ERR_UNSUPPORTED, "disparity range [%d,%d] needs more than the %d labels supported%s", dmin, dmax,
+                            general ? 512 : 2048, general ? " by the float-cost flavour" : "");
+        }
+    const int LPL = LPLv[0] > LPLv[1] ? LPLv[0] : LPLv[1];
     int rc = slot_ensure(ctx, s, w, h, 32 * LPL, p->ndir, general ? 4 : 2);
     if (rc != S2PB_OK) return rc;
 
@@ -1071,22 +1095,31 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
             G.lut = s.lut; G.lo = s.v[vi].lo; G.hi = s.v[vi].hi;
             G.w = w; G.h = h; G.gmin = gminv[vi]; G.cost = p->cost; G.win = p->census_win; G.zoom = 1;
             G.C = (float *)s.v[vi].C;
-            rc = launch_cost_gen(ctx, LPL, G, st);
+            rc = launch_cost_gen(ctx, LPLv[vi], G, st);
+        } else if (wide[vi]) {
+            cost_chunked_kernel<false><<<ctx->sm_count * 8, 256, 0, st>>>(s.v[vi].census, s.v[1 - vi].census_rt, nullptr, w, h, s.v[vi].lo, s.v[vi].hi,
+                                                                        gminv[vi], 32 * LPLv[vi], (__half *)s.v[vi].C);
+            ctx->launches++;
+            rc = cudaGetLastError() == cudaSuccess ? S2PB_OK : fail(S2PB_ERR_CUDA, "cost_chunked_kernel launch failed");
         } else {
-            rc = launch_cost(ctx, LPL, s.v[vi].census, s.v[1 - vi].census_rt, w, h, s.v[vi].lo, s.v[vi].hi, gminv[vi], s.v[vi].C, st);
+            rc = launch_cost(ctx, LPLv[vi], s.v[vi].census, s.v[1 - vi].census_rt, w, h, s.v[vi].lo, s.v[vi].hi, gminv[vi], s.v[vi].C, st);
         }
         if (rc != S2PB_OK) return rc;
     }
     CK(cudaEventRecord(s.ev[2], st));
-    // ---- 8-pass MGM of both views in one persistent launch
-    rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt);
+    // ---- 8-pass MGM of both views in one persistent launch (two when the views' slabs differ in width)
+    if (LPLv[0] == LPLv[1]) rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, wide[0] ? gminv : nullptr);
+    else {
+        rc = launch_aggregate(ctx, s, 1, w, h, LPLv[0], p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, wide[0] ? gminv : nullptr, 0);
+        if (rc == S2PB_OK) rc = launch_aggregate(ctx, s, 1, w, h, LPLv[1], p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, wide[1] ? gminv : nullptr, 1);
+    }
     if (rc != S2PB_OK) return rc;
     CK(cudaEventRecord(s.ev[3], st));
     // ---- WTA + consensus + sub-pixel
     for (int vi = 0; vi < 2; vi++) {
         WtaParams W;
         fill_wta(W, s.v[vi], p->ndir, gminv[vi], p, lut, npix);
-        rc = launch_wta(ctx, LPL, W, st, general);
+        rc = launch_wta(ctx, LPLv[vi], W, st, general, wide[vi]);
         if (rc != S2PB_OK) return rc;
     }
     CK(cudaEventRecord(s.ev[4], st));
@@ -1238,7 +1271,8 @@ extern "C" int s2pb_reserve(s2pb_ctx *ctx, int nslots, int w, int h, int nlabels
     if (!ctx || nslots < 1) return fail(S2PB_ERR_ARG, "bad argument");
     CK(cudaSetDevice(ctx->device));
     int LPL = lpl_for(nlabels);
-    if (LPL < 0) return fail(S2PB_ERR_UNSUPPORTED, "too many labels");
+    if (LPL < 0) LPL = (nlabels + 31) / 32;
+    if (LPL > 64) return fail(S2PB_ERR_UNSUPPORTED, "too many labels");
     int rc = ensure_slots(ctx, nslots);
     if (rc != S2PB_OK) return rc;
     for (int i = 0; i < nslots; i++) {
@@ -1794,25 +1828,29 @@ extern "C" int s2pb_merge_n(s2pb_ctx *ctx, const float *const *inputs, const dou
     CK(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)w * h;
     cudaStream_t st = ctx->slots[0].stream;
-    DevBuf in, o;
-    ALLOC(in, npix * 4 * n);
-    ALLOC(o, npix * 4);
+    // pooled device buffers (kept between calls: a cudaMalloc / cudaFree pair per call costs more than the merge itself)
+    pool_release_all(ctx);
+    struct PoolRef { void *p; float *f() const { return (float *)p; } } in, o;
+    in.p = pool_take(ctx, npix * 4 * n);
+    o.p = pool_take(ctx, npix * 4);
+    if (!in.p || !o.p) { pool_release_all(ctx); return fail(S2PB_ERR_NOMEM, "cudaMalloc failed for the merge buffers"); }
     FusionParams P;
     memset(&P, 0, sizeof P);
     double s = 0;
     for (int k = 0; k < n; k++) {
         if (!inputs[k]) return fail(S2PB_ERR_ARG, "null raster %d", k);
-        P.in[k] = in.as<float>() + npix * k;
+        P.in[k] = in.f() + npix * k;
         CK(cudaMemcpyAsync((void *)P.in[k], inputs[k], npix * 4, cudaMemcpyHostToDevice, st));
         P.offset[k] = offsets[k];
         s += offsets[k];                     // np.mean of a short list: plain left-to-right sum / n
     }
-    P.n = n; P.op = op; P.sub_f32 = sub_f32; P.threshold = threshold; P.mean_offset = s / n; P.npix = npix; P.out = o.as<float>();
+    P.n = n; P.op = op; P.sub_f32 = sub_f32; P.threshold = threshold; P.mean_offset = s / n; P.npix = npix; P.out = o.f();
     fusion_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(P);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, o.p, npix * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    pool_release_all(ctx);
     return S2PB_OK;
 }
 

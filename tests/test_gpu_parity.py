@@ -342,3 +342,30 @@ def test_rejection_mask_matches_reference_programs(engine, oracle):
         d[rng.random(d.shape) < 0.1] = np.nan
         d[:, :3] -= 7.3
         assert np.array_equal(engine.rejection_mask(d, ref, sec), oracle.ref_rejection_mask(d, ref, sec))
+
+
+def test_mgm_multi_level_hull_wider_than_512_labels(engine, oracle):
+    """A pyramid level whose label hull exceeds 512 labels (here the half-pixel pass of a 190-label range with the no-data
+    sentinel sticking out): the reference has no such limit (mgm_costvolume.cc:63-72, one vector per pixel); the engine
+    serves it through the chunk-skipping kernels."""
+    from s2p_b200.engine import default_params
+    h, w, dmin, dmax = 123, 191, -128, 61
+    kw = dict(ndir=2, tsgm=4, census_win=3, P1=8.0, P2=48.0, median=1, lr_mode=0)
+    for seed, nanb in ((5, 0.05), (6, 0.0)):
+        ref, sec, _ = make_pair(h, w, dmin, dmax, seed=seed, nan_border=nanb)
+        out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm_multi", **kw), want_right=True)
+        d, c, dr = oracle.port.mgm_multi(ref, sec, dmin, dmax, oracle.mgm_multi_params(**kw))
+        assert same(out["disp"], d), "%d px differ" % nmismatch(out["disp"], d)
+        assert same(out["conf"], c) and same(out["disp_right"], dr)
+
+
+@pytest.mark.parametrize("dmin,dmax,tsgm", [(-300, 299, 3), (-20, 560, 4), (-700, 450, 2)])
+def test_mgm_more_than_512_labels(engine, oracle, dmin, dmax, tsgm):
+    """algo mgm with a disparity range beyond the 512 labels of the register-resident kernels (up to 2048 are served)"""
+    from s2p_b200.engine import default_params
+    h, w = 37, 640
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=dmax, nan_border=0.03)
+    out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm", tsgm=tsgm), want_right=True)
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(tsgm=tsgm))
+    assert same(out["disp"], d), "%d px differ" % nmismatch(out["disp"], d)
+    assert same(out["conf"], c) and same(out["disp_right"], dr)
