@@ -134,7 +134,9 @@ static int lpl_for(int D)
     for (int o : opts) if (32 * o >= D) return o;
     return -1;
 }
-static int max_bands(int w, int h) { return ((w > h ? w : h) + kNW - 1) / kNW; }
+// stride of the per-pass progress counters: bands hold kNW scanlines in the register-resident kernel, but as few as 4 in the
+// chunk-skipping kernel on slabs wider than 1024 slots (agg_chunked.cuh, ck_warps)
+static int max_bands(int w, int h) { return ((w > h ? w : h) + 3) / 4; }
 
 static int slot_layout(Slot &s, int w, int h, int DP, int ndir, int cbytes, bool allocate)
 {

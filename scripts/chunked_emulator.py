@@ -14,6 +14,10 @@ from oracle import oracle as O
 F = np.float32
 INF = F(np.inf)
 W_, RING, STAGE, R0, PAD, PUBLISH = 16, 4, 4, 8, 4, 8
+if os.environ.get("EMU_WARPS"):          # the configurations of the slabs wider than 512 slots: 8 warps / 2 stages, 4 warps / 2 stages
+    W_ = int(os.environ["EMU_WARPS"])
+    STAGE = int(os.environ.get("EMU_STAGE", 2))
+    R0 = 2 * STAGE
 FIXED = os.environ.get("EMU_BUGGY") != "1"      # EMU_BUGGY=1 reproduces the first version of the kernel (chunk-edge bug)
 FILL_INF = os.environ.get("EMU_FILL_INF") == "1"   # 1: the variant that writes +INF to the skipped chunks of the global volume
 
