@@ -314,13 +314,17 @@ __device__ __forceinline__ float div3_exact(float x)
     return fmaf(r, r3, q0);
 }
 
-// ---- TMA staging (S2PB_AGG_TMA = 1, the f16-cost kernels): a ninth "producer" warp feeds the eight compute warps.
-// Its lanes 0..15 each own one scanline of the band and issue that scanline's cost vector of every pixel step as one bulk copy
-// (cp.async.bulk, the 1-D form of TMA) completing on the step's `full` mbarrier; lane 16 polls the previous band's progress
-// counter and bulk-copies that band's last scanline.  The compute warps wait on `full[step]`, read shared memory, and arrive
-// on `empty[step]`; they carry no staging code, no cp.async group accounting and no ld.acquire poll any more, and warp 0 does the
-// same work as the other seven.  The producer runs up to kStage steps ahead and is not part of the per-step barrier, which
-// becomes a named barrier of the 256 compute threads.
+// ---- TMA staging of the cost slab (S2PB_AGG_TMA = 1, the f16-cost kernels).  Every pixel's cost vector is one contiguous
+// 64 LPL bytes of the [H][W][DP] slab, whatever the direction of the pass: one elected lane per scanline (lane 0 for the
+// warp's upper scanline, lane 16 for the lower one) fetches it with a single bulk copy (cp.async.bulk, the 1-D form of TMA:
+// UBLKCP in SASS) that completes on the mbarrier of that scanline's staging slot, instead of sixteen lanes issuing a 16-byte
+// cp.async each plus the commit / wait-group accounting; the consumers wait on the slot's barrier (SYNCS.PHASECHK.TRYWAIT).
+// A slot is refilled by the warp that read it one step earlier, so program order alone keeps the refill behind the reads.
+// The previous band's scanline (warp 0 only) stays on cp.async: it is gated by the progress counter, not by a slot.
+// A first variant with a dedicated ninth producer warp was measured 3.7x slower (13.1 ms): nine warps of 112 registers do
+// not fit twice in an SM (five warps on one scheduler exceed its 16 K registers), and the single producer, serialising
+// seventeen copies, a proxy fence and the progress poll per step, fell behind the eight consumers
+// (profiles/r02_ncu_aggregate_tma_producer_warp.txt: 66 % of the stall samples in the try_wait loop).
 #ifndef S2PB_AGG_TMA
 #define S2PB_AGG_TMA 0
 #endif
@@ -336,10 +340,6 @@ __device__ __forceinline__ void agg_mbar_expect_tx(unsigned bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void agg_mbar_arrive(unsigned bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void agg_mbar_wait(unsigned bar, unsigned parity)
 {
     // try_wait suspends the thread for a bounded, implementation-defined time per attempt; a watchdog turns a broken
@@ -351,16 +351,17 @@ __device__ __forceinline__ void agg_mbar_wait(unsigned bar, unsigned parity)
         if (!ok && ++spins > (1u << 22)) __trap();
     } while (!ok);
 }
+__device__ __forceinline__ bool agg_elect_one()
+{
+    unsigned p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void agg_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void agg_named_barrier(int id, int threads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
 template <int LPL> struct NbVec {
     float v[LPL];
     float l, r;   // slots just left / right of this lane's, from the neighbouring lanes (INF at the ends)
@@ -394,8 +395,8 @@ template <int LPL, bool GEN = false> struct AggSmem {
     static constexpr size_t r0m_off = r0_off + sizeof(float) * kR0 * DP;              // float [kR0]
     static constexpr size_t cst_off = r0m_off + sizeof(float) * kR0;                  // half | float [kNW][kStage][DP]
     static constexpr size_t wst_off = cst_off + kCostBytes * kNW * kStage * DP;       // float [kNW][kStage]  (GEN: weights)
-    static constexpr size_t bar_off = (wst_off + (GEN ? sizeof(float) * kNW * kStage : 0) + 15) / 16 * 16;   // u64 full[kStage], empty[kStage] (TMA staging)
-    static constexpr size_t bytes = bar_off + ((S2PB_AGG_TMA && !GEN) ? 16 * kStage : 0);
+    static constexpr size_t bar_off = (wst_off + (GEN ? sizeof(float) * kNW * kStage : 0) + 15) / 16 * 16;   // u64 mbarriers of the TMA staging
+    static constexpr size_t bytes = bar_off + ((S2PB_AGG_TMA && !GEN) ? 8 * kNW * kStage : 0);   // full[kNW][kStage]
 };
 
 // smem address (32-bit, shared state space) helpers for cp.async
@@ -453,6 +454,9 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     const long long rowbaseA = pd.base + (long long)sA * pd.strideS;
 
     const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+    // TMA staging: full[scanline][slot], the barrier of a scanline's staging slot (pixel mod kStage)
+    const unsigned bar_s = smem_s + (unsigned)SM::bar_off;
+    const unsigned mybarA = bar_s + 8u * (unsigned)((2 * k) * kStage), mybarB = mybarA + 8u * (unsigned)kStage;
     float *ring = reinterpret_cast<float *>(smem + SM::ring_off);
     float *ringm = reinterpret_cast<float *>(smem + SM::ringm_off);
     float *myring = ring + (size_t)k * kRing * DP + lane * LPL;
@@ -484,6 +488,29 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     const int *prev_progress = (band > 0) ? pd.progress + (band - 1) : nullptr;
     int jp = 0, avail = 0;
 
+    // TMA staging: warp-uniform cursors of the two scanlines; one elected lane arms the slot's barrier and issues the copy
+    const char *tsrcA = reinterpret_cast<const char *>(pd.C) + rowbaseA * CB, *tsrcB = tsrcA + (long long)pd.strideS * CB;
+    const unsigned tdstA = smem_s + (unsigned)SM::cst_off + (unsigned)((2 * k) * kStage * CB), tdstB = tdstA + (unsigned)(kStage * CB);
+    int tjA = 0, tjB = 0;
+    auto stage_tma = [&](const bool doA, const bool doB) {
+        const bool a = doA && liveA && tjA < nI, b = doB && liveB && tjB < nI;
+        if (a || b) {
+            if (agg_elect_one()) {
+                if (a) {
+                    const unsigned slot = (unsigned)(tjA & (kStage - 1));
+                    agg_mbar_expect_tx(mybarA + 8u * slot, (unsigned)CB);
+                    agg_bulk_g2s(tdstA + slot * (unsigned)CB, tsrcA, (unsigned)CB, mybarA + 8u * slot);
+                }
+                if (b) {
+                    const unsigned slot = (unsigned)(tjB & (kStage - 1));
+                    agg_mbar_expect_tx(mybarB + 8u * slot, (unsigned)CB);
+                    agg_bulk_g2s(tdstB + slot * (unsigned)CB, tsrcB, (unsigned)CB, mybarB + 8u * slot);
+                }
+            }
+        }
+        if (doA) { tsrcA += cstep; tjA++; }
+        if (doB) { tsrcB += cstep; tjB++; }
+    };
     auto stage_cost = [&]() {            // stage pixel jc of my scanline's costs
         if (live_st && jc < nI) {
             const unsigned d = cdst + (unsigned)((jc & (kStage - 1)) * CB);
@@ -613,61 +640,6 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         return warp_min_f32(lm);
     };
 
-    // full[q] / empty[q], q = step mod kStage (TMA staging)
-    const unsigned bar_s = smem_s + (unsigned)SM::bar_off;
-    auto full_bar = [&](int t) { return bar_s + 8u * (unsigned)(t & (kStage - 1)); };
-    auto empty_bar = [&](int t) { return bar_s + 8u * (unsigned)(kStage + (t & (kStage - 1))); };
-    if constexpr (TMA) {
-        if (k == kNWC) {
-            // ---- the producer warp.  Production step g loads what compute step g reads: for scanline s of the band the cost
-            // vector of pixel g - skew(s) (lane s), and for the band's first scanline the previous band's vector of pixel
-            // g + LEAD (lane 16; pixels 0 and 1 at g = 0 when LEAD = 1), all completing on full[g].
-            const int sl = lane, skew_l = (sl >> 1) * WSK + (sl & 1) * SKEW;
-            const int sline = band * kNW + sl;
-            const bool live_l = sl < kNW && sline < pd.nS;
-            const char *src = reinterpret_cast<const char *>(pd.C) + (pd.base + (long long)sline * pd.strideS) * CB;
-            const unsigned dst0 = smem_s + (unsigned)SM::cst_off + (unsigned)(sl * kStage * CB);
-            const bool sp = usePrev && band > 0 && (band * kNW < pd.nS) && lane == 16;
-            const long long prevbase0 = pd.base + (long long)(band * kNW - 1) * pd.strideS;      // last scanline of the previous band
-            const char *psrc0 = reinterpret_cast<const char *>(pd.L + prevbase0 * DP);
-            const float *pmsrc0 = pd.Lmin + prevbase0;
-            float *r0m_g = reinterpret_cast<float *>(smem + SM::r0m_off);
-            int jq = 0, av = 0;
-            for (int g = 0; g < nsteps; g++) {
-                if (g >= kStage) agg_mbar_wait(empty_bar(g), (unsigned)(((g / kStage) - 1) & 1));
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's generic-proxy reads precede its async-proxy refill
-                const int pix = g - skew_l;
-                const bool mine = live_l && pix >= 0 && pix < nI;
-                unsigned bytes = mine ? (unsigned)CB : 0u;
-                int np = 0;
-                if (sp) {
-                    np = (LEAD == 1 && g == 0) ? 2 : 1;
-                    if (jq + np > nI) np = nI - jq;
-                    if (np < 0) np = 0;
-                    bytes = (unsigned)(np * DP * 4);
-                    if (np > 0) {
-                        int spins = 0;
-                        while (av < jq + np) {
-                            av = ld_acquire(prev_progress);
-                            if (((++spins) & 1023) == 0 && *(volatile const int *)abort_flag) break;
-                        }
-                        asm volatile("fence.proxy.async;" ::: "memory");       // the acquired stores become visible to the async proxy's reads
-                        for (int q = 0; q < np; q++) r0m_g[(jq + q) & (kR0 - 1)] = __ldcg(pmsrc0 + (long long)(jq + q) * strideI);
-                    }
-                }
-                const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
-                __syncwarp();                                                // lane 16's minima are written before ...
-                if (lane == 0) agg_mbar_expect_tx(full_bar(g), total);      // ... lane 0's arrive releases them
-                __syncwarp();
-                if (mine) agg_bulk_g2s(dst0 + (unsigned)((pix & (kStage - 1)) * CB), src + (long long)pix * cstep, (unsigned)CB, full_bar(g));
-                for (int q = 0; q < np; q++)
-                    agg_bulk_g2s(r0_s + (unsigned)(((jq + q) & (kR0 - 1)) * (DP * 4)), psrc0 + (long long)(jq + q) * lstepb, (unsigned)(DP * 4), full_bar(g));
-                jq += np;
-            }
-            return;
-        }
-    }
-
     NbVec<LPL> x0, x1, x2, h0, h1, h2, wAB;                   // window on A's previous scanline, A's last results, B's last result
 #pragma unroll
     for (int e = 0; e < LPL; e++) x0.v[e] = x1.v[e] = x2.v[e] = h0.v[e] = h1.v[e] = h2.v[e] = wAB.v[e] = 0.f;
@@ -675,10 +647,12 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     h0.l = h0.r = h0.m = h1.l = h1.r = h1.m = h2.l = h2.r = h2.m = wAB.l = wAB.r = wAB.m = 0.f;
 
     // prologue: S groups in flight; group g holds costs(g) and previous-band pixel g+LEAD (+ pixel 0 when LEAD = 1)
-    if constexpr (!TMA) {
-        if (LEAD == 1) stage_prevband();
+    if (LEAD == 1) stage_prevband();
 #pragma unroll 1
-        for (int g = 0; g < S; g++) { stage_cost(); stage_prevband(); cp_async_commit(); }
+    for (int g = 0; g < S; g++) {
+        if constexpr (TMA) stage_tma(true, true); else stage_cost();
+        stage_prevband();
+        cp_async_commit();
     }
 
     // One lock-step pixel step.  Roles at step t: (xB, xC, xE) = window on A's previous scanline at A's
@@ -691,14 +665,17 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         const int iA = t - k * WSK, iB = iA - SKEW;
         const bool actA = FAST || (liveA && iA >= 0 && iA < nI), actB = FAST || (liveB && iB >= 0 && iB < nI);
         NbVec<LPL> &inlineA = useE ? hE : hC;                 // A's result of the previous step
-        if constexpr (!TMA) {
-            if (FAST || iA - rsel * SKEW >= 0) stage_cost();  // my scanline is at pixel jc - S: stage pixel jc
-            if (FAST || iA >= 0) stage_prevband();
-            cp_async_commit();
-        }
+        if constexpr (TMA) stage_tma(FAST || iA >= 0, FAST || iA - SKEW >= 0);
+        else if (FAST || iA - rsel * SKEW >= 0) stage_cost(); // my scanline is at pixel jc - S: stage pixel jc
+        if (FAST || iA >= 0) stage_prevband();
+        if (!TMA || from_r0) cp_async_commit();               // (TMA: only warp 0 still has cp.async traffic, the previous band)
         if (actA || actB) {
-            if constexpr (TMA) agg_mbar_wait(full_bar(t), (unsigned)((t / kStage) & 1));   // the producer's copies of this step have landed
-            else { cp_async_wait<S>(); __syncwarp(); }            // the groups of this step's pixels have landed
+            if (!TMA || from_r0) cp_async_wait<S>();          // the groups of this step's pixels have landed
+            if constexpr (TMA) {                              // ... and the bulk copies of this step's two cost vectors
+                if (actA) agg_mbar_wait(mybarA + 8u * (unsigned)(iA & (kStage - 1)), (unsigned)((iA / kStage) & 1));
+                if (actB) agg_mbar_wait(mybarB + 8u * (unsigned)(iB & (kStage - 1)), (unsigned)((iB / kStage) & 1));
+            }
+            __syncwarp();
             float cA[LPL], cB[LPL], LA[LPL], LB[LPL];
 #pragma unroll
             for (int e = 0; e < LPL; e++) cA[e] = cB[e] = 0.f;
@@ -709,10 +686,6 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             } else if (prevA && actA) {
                 if (useE) { if (iA == 0) fetch_prev(0, xC); if (iA + 1 < nI) fetch_prev(iA + 1, xE); }
                 else fetch_prev(iA, xC);
-            }
-            if constexpr (TMA) {      // everything this step reads from the staging slots is in registers: hand the slots back
-                __syncwarp();
-                if (lane == 0) agg_mbar_arrive(empty_bar(t));
             }
             const bool borderA = (sA == 0) || (iA == 0) || (iA == nI - 1);
             const bool borderB = (iB == 0) || (iB == nI - 1);
@@ -747,14 +720,8 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
                 }
             }
         }
-        if constexpr (TMA) {
-            if (!(actA || actB) && lane == 0) agg_mbar_arrive(empty_bar(t));     // an idle warp still hands the step's slots back
-            if (!SYNC2 || (t & 1)) agg_named_barrier(1, kAggThreads);             // the compute warps only: the producer runs ahead
-            else __syncwarp();
-        } else {
-            if (!SYNC2 || (t & 1)) __syncthreads();
-            else __syncwarp();      // the staging slot the lanes just read is overwritten by the next step's cp.async
-        }
+        if (!SYNC2 || (t & 1)) __syncthreads();
+        else __syncwarp();      // the staging slot the lanes just read is overwritten by the next step's copies
     };
     // a step is FAST for this warp when A is at an interior pixel with B one SKEW behind, also interior
     const bool can_fast = liveA && liveB && prevA;
@@ -815,8 +782,7 @@ template <int LPL, int TSGM> struct AggOcc {
     static constexpr int regs = (LPL <= 4) ? 112 : (two_wide ? 128 : 255);
     static constexpr int ctas = (regs <= 128) ? 2 : 1;
 };
-// threads per CTA: the eight compute warps, plus the producer warp of the TMA staging
-template <bool GEN> struct AggBlock { static constexpr int threads = kAggThreads + ((S2PB_AGG_TMA && !GEN) ? 32 : 0); };
+template <bool GEN> struct AggBlock { static constexpr int threads = kAggThreads; };
 template <int LPL, int TSGM, bool SCALED, bool GEN>
 __global__ void __launch_bounds__(AggBlock<GEN>::threads) __maxnreg__((AggOcc<LPL, TSGM>::regs)) aggregate_kernel(const __grid_constant__ AggParams P)
 {
@@ -835,13 +801,10 @@ __global__ void __launch_bounds__(AggBlock<GEN>::threads) __maxnreg__((AggOcc<LP
         if (band >= pd.nBands) continue;
         if constexpr (S2PB_AGG_TMA && !GEN) {      // fresh full / empty barriers for this band (all phases of the last one are over)
             using SM = AggSmem<LPL, GEN>;
-            if (threadIdx.x == 0) {
-                const unsigned b0 = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)SM::bar_off;
-                for (int q = 0; q < SM::kStage; q++) {
-                    if (!first) { agg_mbar_inval(b0 + 8u * q); agg_mbar_inval(b0 + 8u * (SM::kStage + q)); }
-                    agg_mbar_init(b0 + 8u * q, 1);
-                    agg_mbar_init(b0 + 8u * (SM::kStage + q), kNWC);
-                }
+            if ((int)threadIdx.x < kNW * SM::kStage) {
+                const unsigned b = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)SM::bar_off + 8u * threadIdx.x;
+                if (!first) agg_mbar_inval(b);
+                agg_mbar_init(b, 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             first = false;

@@ -1871,15 +1871,13 @@ extern "C" int s2pb_disp_to_lonlatalt(s2pb_ctx *ctx, double *lonlatalt, float *e
     CK(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)nx * ny, nm = (size_t)w * h;
     cudaStream_t st = ctx->slots[0].stream;
-    DevBuf d_dx, d_dy, d_m, d_mo, d_rpc, d_out, d_err;
+    DevBuf d_dx, d_dy, d_m, d_mo, d_out, d_err;
     ALLOC(d_dx, npix * 4); ALLOC(d_dy, npix * 4); ALLOC(d_m, npix * 4); ALLOC(d_mo, nm * 4);
-    ALLOC(d_rpc, 2 * sizeof(RpcModel)); ALLOC(d_out, npix * 24); ALLOC(d_err, npix * 4);
+    ALLOC(d_out, npix * 24); ALLOC(d_err, npix * 4);
     CK(cudaMemcpyAsync(d_dx.p, dispx, npix * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_dy.p, dispy, npix * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_m.p, msk, npix * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_mo.p, msk_orig, nm * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_rpc.p, rpca, sizeof(RpcModel), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync((char *)d_rpc.p + sizeof(RpcModel), rpcb, sizeof(RpcModel), cudaMemcpyHostToDevice, st));
     TriParams P;
     memset(&P, 0, sizeof P);
     P.dispx = d_dx.as<float>(); P.dispy = d_dy.as<float>(); P.msk = d_m.as<float>(); P.msk_orig = d_mo.as<float>();
@@ -1895,10 +1893,10 @@ extern "C" int s2pb_disp_to_lonlatalt(s2pb_ctx *ctx, double *lonlatalt, float *e
             o[k][6] = (i[3] * i[7] - i[4] * i[6]) / det; o[k][7] = (i[1] * i[6] - i[0] * i[7]) / det; o[k][8] = (i[0] * i[4] - i[1] * i[3]) / det;
         }
     }
-    P.rpca = d_rpc.as<RpcModel>(); P.rpcb = d_rpc.as<RpcModel>() + 1;
+    memcpy(&P.rpca, rpca, sizeof(RpcModel)); memcpy(&P.rpcb, rpcb, sizeof(RpcModel));      // kernel parameters: constant bank
     P.col_min = bbox[0]; P.col_max = bbox[1]; P.row_min = bbox[2]; P.row_max = bbox[3];
     P.lonlatalt = d_out.as<double>(); P.err = d_err.as<float>();
-    dim3 b2(32, 8);
+    dim3 b2(32, 4);
     triangulate_kernel<<<grid2d(nx, ny, b2), b2, 0, st>>>(P);
     ctx->launches++;
     CK(cudaGetLastError());

@@ -24,6 +24,27 @@ class RPCStruct(ctypes.Structure):
                 ("dmval", c_double * 4), ("imval", c_double * 4), ("delta", c_double)]
 
 
+def rpc_from_geotiff_tag(tag, delta=1.0):
+    """RPCStruct from the 92 doubles of a GeoTIFF RPCCoefficientTag (50844): [err_bias, err_rand, line_off, samp_off, lat_off,
+    long_off, height_off, line_scale, samp_scale, lat_scale, long_scale, height_scale, line_num[20], line_den[20], samp_num[20],
+    samp_den[20]] -- filled the way s2p/triangulation.py:42-83 fills its structure from an rpcm model read from the same
+    tag: only the ground->image polynomials exist, the other direction is NaN (the library then iterates, c/rpc.c:378-411)."""
+    t = [float(x) for x in tag]
+    if len(t) != 92:
+        raise ValueError("an RPCCoefficientTag holds 92 doubles, got %d" % len(t))
+    r = RPCStruct()
+    line_off, samp_off, lat_off, lon_off, h_off, line_sc, samp_sc, lat_sc, lon_sc, h_sc = t[2:12]
+    r.offset[0], r.offset[1], r.offset[2] = samp_off, line_off, h_off
+    r.ioffset[0], r.ioffset[1], r.ioffset[2] = lon_off, lat_off, h_off
+    r.scale[0], r.scale[1], r.scale[2] = samp_sc, line_sc, h_sc
+    r.iscale[0], r.iscale[1], r.iscale[2] = lon_sc, lat_sc, h_sc
+    for i in range(20):
+        r.inumy[i], r.ideny[i], r.inumx[i], r.idenx[i] = t[12 + i], t[32 + i], t[52 + i], t[72 + i]
+        r.numx[i] = r.denx[i] = r.numy[i] = r.deny[i] = float("nan")
+    r.delta = delta
+    return r
+
+
 def disp_to_lonlatalt(disp, mask_rect, mask_orig, H1, H2, rpc1, rpc2, img_bbx, dispy=None, engine=None):
     """numpy-level call: -> (lonlatalt (h, w, 3) float64, err (h, w) float32).
     rpc1 / rpc2: any ctypes structure with the layout of ``RPCStruct`` (the reference's own class works)."""

@@ -60,9 +60,16 @@ def main():
     d = np.abs(r["disp"][both] - rect_disp[both])
     print("reference mgm vs rectified_disp.tif: %.2f %% within 0.25 px, median %.2g, NaN mask differs on %.2f %%" % (
         100 * (d <= 0.25).mean(), np.median(d), 100 * (np.isnan(r["disp"]) != np.isnan(rect_disp)).mean()))
+    # the cameras: the RPCCoefficientTag (50844) of the two GeoTIFFs, 92 doubles each
+    from PIL import Image
+    rpcs = []
+    for name in ("img_01.tif", "img_02.tif"):
+        with Image.open(os.path.join(REF, "input_pair", name)) as im:
+            rpcs.append(np.array(im.tag_v2[50844], np.float64))
+    assert rpcs[0].size == 92 and rpcs[1].size == 92
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "real_pair.npz"),
                         crop1=c1.astype(np.uint16), xy1=np.array(xy1), crop2=c2.astype(np.uint16), xy2=np.array(xy2),
-                        H1=H1, H2=H2, rectified_ref=rect_ref, rectified_disp=rect_disp)
+                        H1=H1, H2=H2, rectified_ref=rect_ref, rectified_disp=rect_disp, rpc1=rpcs[0], rpc2=rpcs[1])
 
 
 if __name__ == "__main__":

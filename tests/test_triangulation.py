@@ -69,3 +69,34 @@ def test_matches_reference_library(engine, oracle, with_direct):
     assert np.abs(want[ok][:, :2] - got[ok][:, :2]).max() < 1e-9
     assert np.abs(want[ok][:, 2] - got[ok][:, 2]).max() < 1e-6
     assert np.abs(werr[ok] - gerr[ok]).max() < 1e-4
+
+
+def test_real_rpc_real_disparity(engine, oracle):
+    """Real cameras: the RPCs of the reference's Pleiades fixture (tests/data/input_pair/img_0{1,2}.tif, RPCCoefficientTag,
+    ground->image polynomials only, so every localisation runs the Newton iteration of c/rpc.c:378-411), its rectifying
+    homographies and its shipped disparity map (tests/golden/real_pair.npz), against the reference library."""
+    import os
+    if not oracle.have_ref_triangulation():
+        pytest.skip("oracle/_ref/libdisp_to_h_ref.so not built")
+    from s2p_b200.triangulation import disp_to_lonlatalt, rpc_from_geotiff_tag
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "real_pair.npz"))
+    rpc1, rpc2 = rpc_from_geotiff_tag(z["rpc1"]), rpc_from_geotiff_tag(z["rpc2"])
+    disp = z["rectified_disp"][100:260, 120:360].copy()
+    # the rectified crop starts at (120, 100): move the origin into the homographies
+    T = np.array([[1, 0, -120.0], [0, 1, -100.0], [0, 0, 1]])
+    H1, H2 = T @ z["H1"], T @ z["H2"]
+    mask = np.isfinite(disp).astype(np.float32)
+    disp = np.nan_to_num(disp)
+    bbx = (0.0, 1023.0, 0.0, 1023.0)
+    mo = np.ones((1024, 1024), np.float32)
+    mo[300:340, 500:560] = 0          # a hole in the image-domain mask
+    want, werr = oracle.ref_disp_to_lonlatalt(disp, mask, mo, H1, H2, rpc1, rpc2, bbx)
+    got, gerr = disp_to_lonlatalt(disp, mask, mo, H1, H2, rpc1, rpc2, bbx, engine=engine)
+    assert np.array_equal(np.isnan(want), np.isnan(got)) and np.array_equal(np.isnan(werr), np.isnan(gerr))
+    ok = np.isfinite(want[..., 0])
+    assert ok.mean() > 0.5
+    assert np.abs(want[ok][:, :2] - got[ok][:, :2]).max() < 1e-9
+    assert np.abs(want[ok][:, 2] - got[ok][:, 2]).max() < 1e-6
+    assert np.abs(werr[ok] - gerr[ok]).max() < 1e-4
+    # plausibility: the fixture is over the Reunion island area of the RPC offsets, altitudes within the RPC's height range
+    assert abs(np.nanmedian(got[..., 0]) - z["rpc1"][5]) < 0.2 and abs(np.nanmedian(got[..., 1]) - z["rpc1"][4]) < 0.2
