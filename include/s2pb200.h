@@ -137,6 +137,17 @@ int s2pb_sync(s2pb_ctx *ctx);
 int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh,
                     const double H[9], float *dst, int dw, int dh);
 
+/* ---- steps 3 + 4 of a tile without leaving the device ---- */
+/* rectify_pair's two warps (s2p/rectification.py:379-380 -> common.image_apply_homography) followed by
+ * compute_disparity_map (s2p/__init__.py:184-190) in one call: src1 / src2 are the (crops of the) original images, H1 / H2
+ * the rectifying homographies in their pixel coordinates; both are warped into the matcher's device inputs and matched there.
+ * rect1 / rect2 (nullable): host copies of the rectified pair, for the files later steps read.  Results are identical to
+ * s2pb_homography x 2 followed by s2pb_mgm. */
+int s2pb_rectify_match(s2pb_ctx *ctx, const float *src1, int sw1, int sh1, const double H1[9],
+                       const float *src2, int sw2, int sh2, const double H2[9], int w, int h, int dmin, int dmax,
+                       const s2pb_mgm_params *p, float *rect1, float *rect2, float *disp, float *conf, uint8_t *mask,
+                       float *disp_right);
+
 /* ---- n-view merge (a "next" row of SURVEY.md section 8f) ---------------------- */
 /* s2p.fusion.merge_n (s2p/fusion.py:25-68) from memory to memory: out = op_k(inputs[k] - offsets[k]) +
  * mean(offsets), pixelwise in float64, stored as float32.  op: 0 average_if_close (NaN when

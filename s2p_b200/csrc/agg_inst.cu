@@ -27,10 +27,10 @@ template <> int agg_launch_lpl<kLPL>(int tsgm, const AggParams &P, int sm_count,
 {
     // persistent CTAs, one (or two) per SM; bands are pulled from a global queue in dependency order
     const int total = P.maxBands * P.nPV;
-    dim3 block(AggBlock<false>::threads), block_gen(AggBlock<true>::threads);
+    dim3 block(kAggThreads);
     const bool scaled = P.lut != nullptr;
 #define GO(T) do { int grid = sm_count * AggOcc<kLPL, T>::ctas; if (grid > total) grid = total; \
-                   if (P.general) aggregate_kernel<kLPL, T, false, true><<<grid, block_gen, kSmemGen, st>>>(P); \
+                   if (P.general) aggregate_kernel<kLPL, T, false, true><<<grid, block, kSmemGen, st>>>(P); \
                    else if (scaled) aggregate_kernel<kLPL, T, true, false><<<grid, block, kSmem, st>>>(P); \
                    else aggregate_kernel<kLPL, T, false, false><<<grid, block, kSmem, st>>>(P); } while (0)
     switch (tsgm) {

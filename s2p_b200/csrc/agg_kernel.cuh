@@ -314,54 +314,6 @@ __device__ __forceinline__ float div3_exact(float x)
     return fmaf(r, r3, q0);
 }
 
-// ---- TMA staging of the cost slab (S2PB_AGG_TMA = 1, the f16-cost kernels).  Every pixel's cost vector is one contiguous
-// 64 LPL bytes of the [H][W][DP] slab, whatever the direction of the pass: one elected lane per scanline (lane 0 for the
-// warp's upper scanline, lane 16 for the lower one) fetches it with a single bulk copy (cp.async.bulk, the 1-D form of TMA:
-// UBLKCP in SASS) that completes on the mbarrier of that scanline's staging slot, instead of sixteen lanes issuing a 16-byte
-// cp.async each plus the commit / wait-group accounting; the consumers wait on the slot's barrier (SYNCS.PHASECHK.TRYWAIT).
-// A slot is refilled by the warp that read it one step earlier, so program order alone keeps the refill behind the reads.
-// The previous band's scanline (warp 0 only) stays on cp.async: it is gated by the progress counter, not by a slot.
-// A first variant with a dedicated ninth producer warp was measured 3.7x slower (13.1 ms): nine warps of 112 registers do
-// not fit twice in an SM (five warps on one scheduler exceed its 16 K registers), and the single producer, serialising
-// seventeen copies, a proxy fence and the progress poll per step, fell behind the eight consumers
-// (profiles/r02_ncu_aggregate_tma_producer_warp.txt: 66 % of the stall samples in the try_wait loop).
-#ifndef S2PB_AGG_TMA
-#define S2PB_AGG_TMA 0
-#endif
-__device__ __forceinline__ void agg_mbar_init(unsigned bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void agg_mbar_inval(unsigned bar)
-{
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void agg_mbar_expect_tx(unsigned bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void agg_mbar_wait(unsigned bar, unsigned parity)
-{
-    // try_wait suspends the thread for a bounded, implementation-defined time per attempt; a watchdog turns a broken
-    // producer / consumer protocol into a trap (a context error the host reports) instead of a hung GPU
-    unsigned ok, spins = 0;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok && ++spins > (1u << 22)) __trap();
-    } while (!ok);
-}
-__device__ __forceinline__ bool agg_elect_one()
-{
-    unsigned p;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
-    return p != 0;
-}
-__device__ __forceinline__ void agg_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 template <int LPL> struct NbVec {
     float v[LPL];
     float l, r;   // slots just left / right of this lane's, from the neighbouring lanes (INF at the ends)
@@ -395,8 +347,7 @@ template <int LPL, bool GEN = false> struct AggSmem {
     static constexpr size_t r0m_off = r0_off + sizeof(float) * kR0 * DP;              // float [kR0]
     static constexpr size_t cst_off = r0m_off + sizeof(float) * kR0;                  // half | float [kNW][kStage][DP]
     static constexpr size_t wst_off = cst_off + kCostBytes * kNW * kStage * DP;       // float [kNW][kStage]  (GEN: weights)
-    static constexpr size_t bar_off = (wst_off + (GEN ? sizeof(float) * kNW * kStage : 0) + 15) / 16 * 16;   // u64 mbarriers of the TMA staging
-    static constexpr size_t bytes = bar_off + ((S2PB_AGG_TMA && !GEN) ? 8 * kNW * kStage : 0);   // full[kNW][kStage]
+    static constexpr size_t bytes = wst_off + (GEN ? sizeof(float) * kNW * kStage : 0);
 };
 
 // smem address (32-bit, shared state space) helpers for cp.async
@@ -431,7 +382,6 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     constexpr int SKEW = useE ? 2 : 1;    // scanline s trails scanline s-1 by SKEW pixels
     constexpr int LEAD = useE ? 1 : 0;    // newest previous-scanline pixel needed at position i is i+LEAD
     constexpr int U = useE ? 3 : 2;       // window / history registers rotate with period U: the step loop is unrolled by U
-    constexpr bool TMA = S2PB_AGG_TMA && !GEN;     // producer-warp staging through cp.async.bulk + mbarriers
     using SM = AggSmem<LPL, GEN>;
     using CT = typename std::conditional<GEN, float, __half>::type;      // stored cost element
     constexpr int kStage = SM::kStage, kR0 = SM::kR0, S = kStage - 1, kRing = SM::kRing;
@@ -454,9 +404,6 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     const long long rowbaseA = pd.base + (long long)sA * pd.strideS;
 
     const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
-    // TMA staging: full[scanline][slot], the barrier of a scanline's staging slot (pixel mod kStage)
-    const unsigned bar_s = smem_s + (unsigned)SM::bar_off;
-    const unsigned mybarA = bar_s + 8u * (unsigned)((2 * k) * kStage), mybarB = mybarA + 8u * (unsigned)kStage;
     float *ring = reinterpret_cast<float *>(smem + SM::ring_off);
     float *ringm = reinterpret_cast<float *>(smem + SM::ringm_off);
     float *myring = ring + (size_t)k * kRing * DP + lane * LPL;
@@ -488,29 +435,6 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     const int *prev_progress = (band > 0) ? pd.progress + (band - 1) : nullptr;
     int jp = 0, avail = 0;
 
-    // TMA staging: warp-uniform cursors of the two scanlines; one elected lane arms the slot's barrier and issues the copy
-    const char *tsrcA = reinterpret_cast<const char *>(pd.C) + rowbaseA * CB, *tsrcB = tsrcA + (long long)pd.strideS * CB;
-    const unsigned tdstA = smem_s + (unsigned)SM::cst_off + (unsigned)((2 * k) * kStage * CB), tdstB = tdstA + (unsigned)(kStage * CB);
-    int tjA = 0, tjB = 0;
-    auto stage_tma = [&](const bool doA, const bool doB) {
-        const bool a = doA && liveA && tjA < nI, b = doB && liveB && tjB < nI;
-        if (a || b) {
-            if (agg_elect_one()) {
-                if (a) {
-                    const unsigned slot = (unsigned)(tjA & (kStage - 1));
-                    agg_mbar_expect_tx(mybarA + 8u * slot, (unsigned)CB);
-                    agg_bulk_g2s(tdstA + slot * (unsigned)CB, tsrcA, (unsigned)CB, mybarA + 8u * slot);
-                }
-                if (b) {
-                    const unsigned slot = (unsigned)(tjB & (kStage - 1));
-                    agg_mbar_expect_tx(mybarB + 8u * slot, (unsigned)CB);
-                    agg_bulk_g2s(tdstB + slot * (unsigned)CB, tsrcB, (unsigned)CB, mybarB + 8u * slot);
-                }
-            }
-        }
-        if (doA) { tsrcA += cstep; tjA++; }
-        if (doB) { tsrcB += cstep; tjB++; }
-    };
     auto stage_cost = [&]() {            // stage pixel jc of my scanline's costs
         if (live_st && jc < nI) {
             const unsigned d = cdst + (unsigned)((jc & (kStage - 1)) * CB);
@@ -649,11 +573,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     // prologue: S groups in flight; group g holds costs(g) and previous-band pixel g+LEAD (+ pixel 0 when LEAD = 1)
     if (LEAD == 1) stage_prevband();
 #pragma unroll 1
-    for (int g = 0; g < S; g++) {
-        if constexpr (TMA) stage_tma(true, true); else stage_cost();
-        stage_prevband();
-        cp_async_commit();
-    }
+    for (int g = 0; g < S; g++) { stage_cost(); stage_prevband(); cp_async_commit(); }
 
     // One lock-step pixel step.  Roles at step t: (xB, xC, xE) = window on A's previous scanline at A's
     // pixel-1, pixel, pixel+1; hNew = A's result of U steps ago (B's "B" neighbour; overwritten with A's new
@@ -665,16 +585,11 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         const int iA = t - k * WSK, iB = iA - SKEW;
         const bool actA = FAST || (liveA && iA >= 0 && iA < nI), actB = FAST || (liveB && iB >= 0 && iB < nI);
         NbVec<LPL> &inlineA = useE ? hE : hC;                 // A's result of the previous step
-        if constexpr (TMA) stage_tma(FAST || iA >= 0, FAST || iA - SKEW >= 0);
-        else if (FAST || iA - rsel * SKEW >= 0) stage_cost(); // my scanline is at pixel jc - S: stage pixel jc
+        if (FAST || iA - rsel * SKEW >= 0) stage_cost();      // my scanline is at pixel jc - S: stage pixel jc
         if (FAST || iA >= 0) stage_prevband();
-        if (!TMA || from_r0) cp_async_commit();               // (TMA: only warp 0 still has cp.async traffic, the previous band)
+        cp_async_commit();
         if (actA || actB) {
-            if (!TMA || from_r0) cp_async_wait<S>();          // the groups of this step's pixels have landed
-            if constexpr (TMA) {                              // ... and the bulk copies of this step's two cost vectors
-                if (actA) agg_mbar_wait(mybarA + 8u * (unsigned)(iA & (kStage - 1)), (unsigned)((iA / kStage) & 1));
-                if (actB) agg_mbar_wait(mybarB + 8u * (unsigned)(iB & (kStage - 1)), (unsigned)((iB / kStage) & 1));
-            }
+            cp_async_wait<S>();                               // the groups of this step's pixels have landed
             __syncwarp();
             float cA[LPL], cB[LPL], LA[LPL], LB[LPL];
 #pragma unroll
@@ -721,7 +636,7 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
             }
         }
         if (!SYNC2 || (t & 1)) __syncthreads();
-        else __syncwarp();      // the staging slot the lanes just read is overwritten by the next step's copies
+        else __syncwarp();      // the staging slot the lanes just read is overwritten by the next step's cp.async
     };
     // a step is FAST for this warp when A is at an interior pixel with B one SKEW behind, also interior
     const bool can_fast = liveA && liveB && prevA;
@@ -782,14 +697,12 @@ template <int LPL, int TSGM> struct AggOcc {
     static constexpr int regs = (LPL <= 4) ? 112 : (two_wide ? 128 : 255);
     static constexpr int ctas = (regs <= 128) ? 2 : 1;
 };
-template <bool GEN> struct AggBlock { static constexpr int threads = kAggThreads; };
 template <int LPL, int TSGM, bool SCALED, bool GEN>
-__global__ void __launch_bounds__(AggBlock<GEN>::threads) __maxnreg__((AggOcc<LPL, TSGM>::regs)) aggregate_kernel(const __grid_constant__ AggParams P)
+__global__ void __launch_bounds__(kAggThreads) __maxnreg__((AggOcc<LPL, TSGM>::regs)) aggregate_kernel(const __grid_constant__ AggParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_item;
     const int total = P.maxBands * P.nPV;
-    bool first = true;
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(P.next_item, 1);
         __syncthreads();
@@ -799,17 +712,6 @@ __global__ void __launch_bounds__(AggBlock<GEN>::threads) __maxnreg__((AggOcc<LP
         const int band = item / P.nPV, pvi = item - band * P.nPV;
         const PassDesc &pd = P.pv[pvi];
         if (band >= pd.nBands) continue;
-        if constexpr (S2PB_AGG_TMA && !GEN) {      // fresh full / empty barriers for this band (all phases of the last one are over)
-            using SM = AggSmem<LPL, GEN>;
-            if ((int)threadIdx.x < kNW * SM::kStage) {
-                const unsigned b = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)SM::bar_off + 8u * threadIdx.x;
-                if (!first) agg_mbar_inval(b);
-                agg_mbar_init(b, 1);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            }
-            first = false;
-            __syncthreads();
-        }
         if (pd.type == 0) run_band<LPL, TSGM, 0, SCALED, GEN>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, smem);
         else run_band<LPL, TSGM, 1, SCALED, GEN>(pd, band, P.P1, P.P2, P.lut, P.abort_flag, smem);
     }

@@ -1770,11 +1770,11 @@ static int map_image(s2pb_ctx *ctx, cudaStream_t st, const float *d_src, int w, 
     return S2PB_OK;     // buffers stay taken until the whole warp is done (stream order protects them)
 }
 
-// `homography im -h "..." out w h` (3rdparty/homography/main.cpp:65-177) from memory to memory
-extern "C" int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh, const double H[9], float *dst, int dw, int dh)
+// The part of `homography im -h "..." out w h` (3rdparty/homography/main.cpp:65-177) between reading and writing: needed
+// region of the host image `src`, upload of that region only, crop compensation of H, warp into the DEVICE image d_out.
+// Asynchronous on `st`; the pooled buffers stay taken until the caller releases them.
+static int warp_host_to_device(s2pb_ctx *ctx, cudaStream_t st, const float *src, int sw, int sh, const double H[9], float *d_out, int dw, int dh)
 {
-    if (!ctx || !src || !H || !dst || sw < 1 || sh < 1 || dw < 1 || dh < 1) return fail(S2PB_ERR_ARG, "bad argument");
-    CK(cudaSetDevice(ctx->device));
     // needed ROI of the source: pre-image of the output corners, integer bounding box, clipped (main.cpp:29-55,94-127)
     double Hi[9];
     {
@@ -1804,17 +1804,63 @@ extern "C" int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh, 
     const double T[9] = {1, 0, (double)x, 0, 1, (double)y, 0, 0, 1};
     double Hc[9];
     for (int r = 0; r < 3; r++) for (int q = 0; q < 3; q++) Hc[3 * r + q] = H[3 * r] * T[q] + H[3 * r + 1] * T[3 + q] + H[3 * r + 2] * T[6 + q];
+    float *roi = (float *)pool_take(ctx, (size_t)w * h * 4);
+    if (!roi) return fail(S2PB_ERR_NOMEM, "cudaMalloc failed for the warp buffers");
+    CK(cudaMemcpy2DAsync(roi, (size_t)w * 4, src + (size_t)y * sw + x, (size_t)sw * 4, (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice, st));
+    return map_image(ctx, st, roi, w, h, Hc, d_out, dw, dh, true, 0);
+}
+
+// `homography im -h "..." out w h` (3rdparty/homography/main.cpp:65-177) from memory to memory
+extern "C" int s2pb_homography(s2pb_ctx *ctx, const float *src, int sw, int sh, const double H[9], float *dst, int dw, int dh)
+{
+    if (!ctx || !src || !H || !dst || sw < 1 || sh < 1 || dw < 1 || dh < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->slots[0].stream;
     pool_release_all(ctx);
-    float *roi = (float *)pool_take(ctx, (size_t)w * h * 4), *out = (float *)pool_take(ctx, (size_t)dw * dh * 4);
-    if (!roi || !out) { pool_release_all(ctx); return fail(S2PB_ERR_NOMEM, "cudaMalloc failed for the warp buffers"); }
-    CK(cudaMemcpy2DAsync(roi, (size_t)w * 4, src + (size_t)y * sw + x, (size_t)sw * 4, (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice, st));
-    int rc = map_image(ctx, st, roi, w, h, Hc, out, dw, dh, true, 0);
+    float *out = (float *)pool_take(ctx, (size_t)dw * dh * 4);
+    if (!out) { pool_release_all(ctx); return fail(S2PB_ERR_NOMEM, "cudaMalloc failed for the warp buffers"); }
+    int rc = warp_host_to_device(ctx, st, src, sw, sh, H, out, dw, dh);
     if (rc != S2PB_OK) { cudaStreamSynchronize(st); pool_release_all(ctx); return rc; }
     CK(cudaMemcpyAsync(dst, out, (size_t)dw * dh * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     pool_release_all(ctx);
     return S2PB_OK;
+}
+
+// Steps 3 and 4 of a tile in one call (s2p/__init__.py:147-155 rectify_pair's two warps, :184-190 compute_disparity_map): both
+// images are warped straight into the matcher's device inputs and matched there; the rectified pair never travels through
+// files or host memory unless the caller asks for a copy (rect1 / rect2).
+extern "C" int s2pb_rectify_match(s2pb_ctx *ctx, const float *src1, int sw1, int sh1, const double H1[9],
+                                  const float *src2, int sw2, int sh2, const double H2[9], int w, int h, int dmin, int dmax,
+                                  const s2pb_mgm_params *p, float *rect1, float *rect2, float *disp, float *conf, uint8_t *mask,
+                                  float *disp_right)
+{
+    if (!ctx || !src1 || !src2 || !H1 || !H2 || !disp || !conf || sw1 < 1 || sh1 < 1 || sw2 < 1 || sh2 < 1) return fail(S2PB_ERR_ARG, "bad argument");
+    int rc = check_params(p, w, h, dmin, dmax);
+    if (rc != S2PB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    cudaStream_t st = s.stream;
+    const size_t npix = (size_t)w * h;
+    rc = slot_io_ensure(s, npix);
+    if (rc != S2PB_OK) return rc;
+    set_deadline(ctx, p->timeout_ms);
+    pool_release_all(ctx);
+    rc = warp_host_to_device(ctx, st, src1, sw1, sh1, H1, s.d_in[0], w, h);
+    if (rc == S2PB_OK) rc = warp_host_to_device(ctx, st, src2, sw2, sh2, H2, s.d_in[1], w, h);
+    if (rc != S2PB_OK) { cudaStreamSynchronize(st); pool_release_all(ctx); return rc; }
+    if (rect1) CK(cudaMemcpyAsync(rect1, s.d_in[0], npix * 4, cudaMemcpyDeviceToHost, st));
+    if (rect2) CK(cudaMemcpyAsync(rect2, s.d_in[1], npix * 4, cudaMemcpyDeviceToHost, st));
+    rc = mgm_enqueue(ctx, s, s.d_in[0], s.d_in[1], w, h, dmin, dmax, p, s.d_disp, s.d_conf, mask ? s.d_mask : nullptr,
+                     disp_right ? s.d_dispR : nullptr, st, -1);
+    if (rc != S2PB_OK) { cudaStreamSynchronize(st); pool_release_all(ctx); return rc; }
+    CK(cudaMemcpyAsync(disp, s.d_disp, npix * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(conf, s.d_conf, npix * 4, cudaMemcpyDeviceToHost, st));
+    if (mask) CK(cudaMemcpyAsync(mask, s.d_mask, npix, cudaMemcpyDeviceToHost, st));
+    if (disp_right) CK(cudaMemcpyAsync(disp_right, s.d_dispR, npix * 4, cudaMemcpyDeviceToHost, st));
+    rc = wait_with_timeout(ctx, st);
+    pool_release_all(ctx);
+    return rc;
 }
 
 // ------------------------------------------------------------------ n-view merge (section 8f)

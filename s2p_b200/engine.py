@@ -157,6 +157,27 @@ class Engine:
                                            Hm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _fp(out), int(w), int(h)))
         return out
 
+    def rectify_match(self, src1, H1, src2, H2, w, h, dmin, dmax, params=None, want_rect=True, want_right=False):
+        """rectify_pair's two warps + compute_disparity_map in one call, the rectified pair staying on the device
+        (s2p/__init__.py:147-155,184-190).  -> dict(disp, conf, mask[, rect1, rect2][, disp_right])"""
+        src1, src2 = _f32(src1), _f32(src2)
+        p = params or default_params("mgm")
+        w, h = int(w), int(h)
+        dp = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(9)).ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        Ha, Hb = np.ascontiguousarray(np.asarray(H1, np.float64).reshape(9)), np.ascontiguousarray(np.asarray(H2, np.float64).reshape(9))
+        out = dict(disp=np.empty((h, w), np.float32), conf=np.empty((h, w), np.float32), mask=np.empty((h, w), np.uint8))
+        if want_rect:
+            out["rect1"], out["rect2"] = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+        if want_right:
+            out["disp_right"] = np.empty((h, w), np.float32)
+        nul = ctypes.POINTER(ctypes.c_float)()
+        _lib.check(self._L.s2pb_rectify_match(
+            self._ctx, _fp(src1), src1.shape[1], src1.shape[0], Ha.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+            _fp(src2), src2.shape[1], src2.shape[0], Hb.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), w, h, int(dmin), int(dmax),
+            ctypes.byref(p), _fp(out["rect1"]) if want_rect else nul, _fp(out["rect2"]) if want_rect else nul, _fp(out["disp"]),
+            _fp(out["conf"]), out["mask"].ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _fp(out["disp_right"]) if want_right else nul))
+        return out
+
     # ------------------------------------------------------------------ n-view merge
     FUSION_OPS = {"average_if_close": 0, "np.nanmedian": 1, "np.nanmean": 2, "np.nanmin": 3, "np.nanmax": 4,
                   "np.median": 5, "np.mean": 6, "np.min": 7, "np.max": 8, "np.amin": 7, "np.amax": 8}

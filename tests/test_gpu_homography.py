@@ -128,3 +128,29 @@ def test_real_imagery_chain_reproduces_reference_disparity(engine):
     assert both.mean() > 0.9
     assert (np.abs(out["disp"][both] - want[both]) <= 0.25).mean() >= 0.995
     assert (np.isnan(out["disp"]) != np.isnan(want)).mean() < 0.01
+
+
+def test_fused_rectify_and_match_equals_the_file_path(engine, tmp_path):
+    """s2p_b200.fused.rectify_and_match (both warps and the matcher in one device call, the rectified pair never leaving the
+    GPU) writes the same five files, bit for bit, as image_apply_homography x 2 followed by compute_disparity_map."""
+    from s2p_b200 import block_matching as bm, common, fused, rasterio_compat as rio
+    z, _, _ = _real_pair()
+    a, b = str(tmp_path / "img_01.tif"), str(tmp_path / "img_02.tif")
+    rio.write_float_tiff(a, z["crop1"].astype(np.float32))
+    rio.write_float_tiff(b, z["crop2"].astype(np.float32))
+    comp = lambda Hm, xy: np.asarray(Hm, np.float64) @ np.array([[1, 0, xy[0]], [0, 1, xy[1]], [0, 0, 1.0]])
+    H1, H2 = comp(z["H1"], z["xy1"]), comp(z["H2"], z["xy2"])
+    h, w = z["rectified_ref"].shape
+    for algo in ("mgm", "mgm_multi"):
+        d1 = tmp_path / ("two_step_" + algo)
+        d2 = tmp_path / ("fused_" + algo)
+        d1.mkdir(); d2.mkdir()
+        p = lambda d, n: str(d / n)
+        common.image_apply_homography(p(d1, "rectified_ref.tif"), a, H1, w, h)
+        common.image_apply_homography(p(d1, "rectified_sec.tif"), b, H2, w, h)
+        bm.compute_disparity_map(p(d1, "rectified_ref.tif"), p(d1, "rectified_sec.tif"), p(d1, "rectified_disp.tif"), p(d1, "rectified_mask.png"),
+                                 algo, -41, 30)
+        fused.rectify_and_match(p(d2, "rectified_ref.tif"), p(d2, "rectified_sec.tif"), p(d2, "rectified_disp.tif"), p(d2, "rectified_mask.png"),
+                                a, b, H1, H2, w, h, algo, -41, 30)
+        for name in ("rectified_ref.tif", "rectified_sec.tif", "rectified_disp.tif", "rectified_disp_confidence.tif", "rectified_mask.png"):
+            assert np.array_equal(rio.read_band(p(d1, name)), rio.read_band(p(d2, name)), equal_nan=True), (algo, name)
