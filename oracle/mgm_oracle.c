@@ -534,6 +534,25 @@ void orc_remove_small_cc(int w, int h, const float *in, float *out, int minarea,
 /* ------------------------------------------------------- one-scale driver */
 
 /* One view of mgm_call (mgm_multiscale.cc:161-305): volume, aggregation, refinement, /ZOOM. */
+/* compute_PKR_confidence (mgm_costvolume.cc:199-214): ratio of the second minimum of S -- over the labels of the pixel's range
+ * more than 2 away from the winner -- to the first, the winner being the integer WTA label (it runs before the sub-pixel
+ * refinement, mgm_multiscale.cc:247).  Each mgm_call overwrites the image of the call before (img_dict, :247,:297): the caller gets
+ * the last call's.  g_pkr[view] = destination or NULL. */
+static float *g_pkr[2] = {NULL, NULL};
+static int g_view = 0;
+static void orc_pkr(const float *S, const float *disp, const int *lo, const int *hi, int npix, int gmin, int D, float *out)
+{
+    for (int i = 0; i < npix; i++) {
+        float currdisp = roundf(disp[i]);
+        int k0 = (int)currdisp - gmin;
+        float firstmin = (k0 >= lo[i] - gmin && k0 <= hi[i] - gmin) ? S[(size_t)i * D + k0] : ORC_INF;   /* Dvec[]: +inf outside the range */
+        float secondmin = ORC_INF;
+        for (int o = lo[i]; o <= hi[i]; o++)
+            if (fabsf((float)o - currdisp) > 2 && secondmin > S[(size_t)i * D + (o - gmin)]) secondmin = S[(size_t)i * D + (o - gmin)];
+        out[i] = secondmin / fmax(firstmin, 0.01);
+    }
+}
+
 static void orc_view(const float *u, const float *v, int w, int h, const float *dminI, const float *dmaxI,
                      const orc_params *P, int zoom, const float *wgt, float *disp, float *cost, float *conf)
 {
@@ -557,6 +576,7 @@ static void orc_view(const float *u, const float *v, int w, int h, const float *
     orc_costvolume(u, v, w, h, lo, hi, gmin, D, P->census_win, zoom, P->dct_shift, P->cost, C);
     float P1 = P->P1 / zoom;                                  /* mgm_multiscale.cc:194-202 */
     orc_aggregate_w(C, lo, hi, w, h, gmin, D, P1, P->P2, P->ndir, P->tsgm, P->fix_overcount, wgt, S, disp, cost, conf);
+    if (g_pkr[g_view]) orc_pkr(S, disp, lo, hi, npix, gmin, D, g_pkr[g_view]);
     orc_refine(S, lo, hi, npix, gmin, D, P->refine, disp, cost);
     for (int i = 0; i < npix; i++) disp[i] /= (float)zoom;     /* :253 */
     free(C); free(S); free(lo); free(hi);
@@ -579,8 +599,9 @@ void orc_mgm_call_w(const float *u, const float *v, int w, int h,
     int npix = w * h;
     float *cl = malloc(sizeof(float) * npix), *cr = malloc(sizeof(float) * npix);
     float *confR = malloc(sizeof(float) * npix);
-    orc_view(u, v, w, h, dminL, dmaxL, P, zoom, wl, dl, cl, confL);
-    orc_view(v, u, w, h, dminR, dmaxR, P, zoom, wr, dr, cr, confR);
+    g_view = 0; orc_view(u, v, w, h, dminL, dmaxL, P, zoom, wl, dl, cl, confL);
+    g_view = 1; orc_view(v, u, w, h, dminR, dmaxR, P, zoom, wr, dr, cr, confR);
+    g_view = 0;
     if (P->median) {                                          /* :312-315 */
         float *t = malloc(sizeof(float) * npix);
         orc_median(dl, t, w, h, P->median); memcpy(dl, t, sizeof(float) * npix);
@@ -668,6 +689,21 @@ int orc_mgm_w(const float *im1, const float *im2, int w, int h, int dmin, int dm
     if (dispR) memcpy(dispR, dr, sizeof(float) * npix);
     free(u); free(v); free(a); free(b); free(c); free(d); free(dr);
     return 0;
+}
+
+/* -confidence_pkrL / -confidence_pkrR of either binary: run `multi ? orc_mgm_multi_w : orc_mgm_w` with the PKR images captured
+ * (pkrL / pkrR: w*h floats).  Every mgm_call overwrites the images of the call before; in mgm_multi the ones written are those of
+ * the full-resolution ZOOM = 1 call, because the SUBPIX pass runs on a `param` of its own (main_mgm_multi.cc:207,240-251). */
+int orc_mgm_multi_w(const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+                    const orc_params *P, const float *wl, const float *wr, float *disp, float *conf, float *dispR);
+int orc_mgm_pkr(const float *im1, const float *im2, int w, int h, int dmin, int dmax, const orc_params *P, int multi,
+                float *disp, float *conf, float *dispR, float *pkrL, float *pkrR)
+{
+    g_pkr[0] = pkrL; g_pkr[1] = pkrR;
+    int r = multi ? orc_mgm_multi_w(im1, im2, w, h, dmin, dmax, P, NULL, NULL, disp, conf, dispR)
+                  : orc_mgm_w(im1, im2, w, h, dmin, dmax, P, NULL, NULL, disp, conf, dispR);
+    g_pkr[0] = g_pkr[1] = NULL;
+    return r;
 }
 
 /* ------------------------------------------------------------ `mgm_multi` */
@@ -826,6 +862,7 @@ int orc_mgm_multi_w(const float *im1, const float *im2, int w, int h, int dmin, 
         if (isnan(im2[i])) { c[i] = dmin; d[i] = dmin + 1; }
     }
     orc_recursive(u, v, w, h, a, b, c, d, P, 1, P->scales, 0, wl, wr, disp, dr, conf);
+    g_pkr[0] = g_pkr[1] = NULL;      /* the SUBPIX pass runs on its own `param` (main_mgm_multi.cc:207): the images written come from the call above */
     if (P->subpix > 1) {                                       /* :203-209 */
         orc_update_dmin_dmax(disp, w, h, a, b, a, b, w, h, 2, 4);
         orc_update_dmin_dmax(dr, w, h, c, d, c, d, w, h, 2, 4);

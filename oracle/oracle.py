@@ -150,6 +150,16 @@ class port:
         return disp, conf, dispR
 
     @staticmethod
+    def mgm_pkr(im1, im2, dmin, dmax, params=None, multi=False):
+        """-> disp, conf, dispR, pkrL, pkrR: as `mgm` / `mgm_multi` with -confidence_pkrL / -confidence_pkrR"""
+        im1, im2 = _f32(im1), _f32(im2)
+        h, w = im1.shape
+        out = [np.empty((h, w), np.float32) for _ in range(5)]
+        lib().orc_mgm_pkr(_p(im1), _p(im2), w, h, int(dmin), int(dmax), ctypes.byref(params or (mgm_multi_params() if multi else mgm_params())),
+                          1 if multi else 0, *[_p(o) for o in out])
+        return tuple(out)
+
+    @staticmethod
     def rejection_mask(disp, im1, im2):
         disp, im1, im2 = _f32(disp), _f32(im1), _f32(im2)
         h, w = disp.shape
@@ -217,7 +227,7 @@ def _env(params, threads):
 _REFINE = {0: "none", 1: "vfit", 2: "parabola"}
 
 
-def run_ref(im1, im2, dmin, dmax, params, threads=1, extra_env=None, workdir=None, binary=None, wl=None, wr=None):
+def run_ref(im1, im2, dmin, dmax, params, threads=1, extra_env=None, workdir=None, binary=None, wl=None, wr=None, want_pkr=False):
     """Run oracle/_ref/mgm (params.scales < 0) or mgm_multi on in-memory images.
     -> dict(disp, conf, dispR, seconds).  OMP_NUM_THREADS=1 is the parity oracle."""
     import time
@@ -238,6 +248,9 @@ def run_ref(im1, im2, dmin, dmax, params, threads=1, extra_env=None, workdir=Non
         write_pfm(pl, wl)
         write_pfm(pr, wr)
         argv += ["-wl", pl, "-wr", pr]
+    pk = [os.path.join(tmp, n) for n in ("pkrL.pfm", "pkrR.pfm")]
+    if want_pkr:
+        argv += ["-confidence_pkrL", pk[0], "-confidence_pkrR", pk[1]]
     argv += ["-confidence_consensusL", c, "-Rd", r, a, b, d]
     env = _env(params, threads)
     if extra_env:
@@ -246,6 +259,8 @@ def run_ref(im1, im2, dmin, dmax, params, threads=1, extra_env=None, workdir=Non
     subprocess.run(argv, env=env, check=True, stdout=subprocess.DEVNULL, cwd=tmp)
     dt = time.perf_counter() - t0
     out = dict(disp=read_pfm(d), conf=read_pfm(c), dispR=read_pfm(r), seconds=dt, workdir=tmp)
+    if want_pkr:
+        out["pkrL"], out["pkrR"] = read_pfm(pk[0]), read_pfm(pk[1])
     return out
 
 

@@ -5,10 +5,11 @@
 #include "agg_kernel.cuh"
 
 namespace s2pb {
-template <int LPL> int agg_launch_lpl(int tsgm, const AggParams &P, int sm_count, cudaStream_t st);
+template <int LPL> int agg_launch_lpl(int tsgm, const AggParams &P, int sm_count, cudaStream_t st, int ctas_per_sm);
 template <int LPL> int agg_configure_lpl();
 int agg_configure();                                   // 0 ok
-int agg_launch(int LPL, int tsgm, const AggParams &P, int sm_count, cudaStream_t st);   // 0 ok, -1 CUDA error, -2 unsupported
+// ctas_per_sm > 0 caps the persistent CTAs per SM (two launches meant to share the SMs); 0 ok, -1 CUDA error, -2 unsupported
+int agg_launch(int LPL, int tsgm, const AggParams &P, int sm_count, cudaStream_t st, int ctas_per_sm = 0);
 // experimental chunk-skipping aggregation (agg_chunked.cuh); -2 = shape not served, use the dense kernel
 struct ChunkedParams;
 int agg_chunked_configure();

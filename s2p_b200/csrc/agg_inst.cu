@@ -23,13 +23,14 @@ template <> int agg_configure_lpl<kLPL>()
     return 0;
 }
 
-template <> int agg_launch_lpl<kLPL>(int tsgm, const AggParams &P, int sm_count, cudaStream_t st)
+template <> int agg_launch_lpl<kLPL>(int tsgm, const AggParams &P, int sm_count, cudaStream_t st, int ctas_per_sm)
 {
     // persistent CTAs, one (or two) per SM; bands are pulled from a global queue in dependency order
     const int total = P.maxBands * P.nPV;
     dim3 block(kAggThreads);
     const bool scaled = P.lut != nullptr;
-#define GO(T) do { int grid = sm_count * AggOcc<kLPL, T>::ctas; if (grid > total) grid = total; \
+#define GO(T) do { int per = AggOcc<kLPL, T>::ctas; if (ctas_per_sm > 0 && ctas_per_sm < per) per = ctas_per_sm; \
+                   int grid = sm_count * per; if (grid > total) grid = total; \
                    if (P.general) aggregate_kernel<kLPL, T, false, true><<<grid, block, kSmemGen, st>>>(P); \
                    else if (scaled) aggregate_kernel<kLPL, T, true, false><<<grid, block, kSmem, st>>>(P); \
                    else aggregate_kernel<kLPL, T, false, false><<<grid, block, kSmem, st>>>(P); } while (0)

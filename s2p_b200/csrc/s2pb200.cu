@@ -87,6 +87,8 @@ struct Slot {
     char *arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // the right view's aggregation when the two views' slabs differ in width (runs beside the left one)
+    cudaEvent_t fork = nullptr, join = nullptr;
     cudaEvent_t ev[S2PB_T_COUNT + 1] = {};
     cudaEvent_t done = nullptr;
     bool timed = false;
@@ -235,6 +237,9 @@ static int slot_host_ensure(Slot &s, size_t npix)
 static int slot_init(s2pb_ctx *ctx, Slot &s)
 {
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
     for (auto &e : s.ev) CK(cudaEventCreate(&e));
     CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     return S2PB_OK;
@@ -294,6 +299,9 @@ extern "C" void s2pb_destroy(s2pb_ctx *ctx)
         if (s.h_in[0]) cudaFreeHost(s.h_in[0]);
         for (auto &e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.fork) cudaEventDestroy(s.fork);
+        if (s.join) cudaEventDestroy(s.join);
+        if (s.stream2) { cudaStreamSynchronize(s.stream2); cudaStreamDestroy(s.stream2); }
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (auto &b : ctx->pool) cudaFree(b.p);
@@ -467,7 +475,7 @@ static bool chunked_cost_enabled(int DP) { return DP > 512 || (chunked_mode() ==
 // gminv: label of slot 0 per view (only needed by the chunk-skipping kernel; nullptr = dense kernel)
 static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, int LPL, float P1, float P2, int ndir, int tsgm,
                             const float *lut, cudaStream_t st, bool general = false, const float *const *wgt = nullptr,
-                            const int *gminv = nullptr, int first_view = 0)
+                            const int *gminv = nullptr, int first_view = 0, int ctas_per_sm = 0)
 {
     AggParams P;
     memset(&P, 0, sizeof P);
@@ -484,9 +492,10 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
             if (pd.nBands > P.maxBands) P.maxBands = pd.nBands;
         }
     }
-    P.P1 = P1; P.P2 = P2; P.next_item = s.next_item; P.abort_flag = ctx->abort_flag; P.lut = general ? nullptr : lut;
+    int *counter = s.next_item + 16 * first_view;          // two launches may be in flight at once: one work counter each
+    P.P1 = P1; P.P2 = P2; P.next_item = counter; P.abort_flag = ctx->abort_flag; P.lut = general ? nullptr : lut;
     P.general = general ? 1 : 0;
-    CK(cudaMemsetAsync(s.next_item, 0, 4, st));
+    CK(cudaMemsetAsync(counter, 0, 4, st));
     if (!general && gminv && chunked_enabled(32 * LPL)) {
         ChunkedParams Q;
         memset(&Q, 0, sizeof Q);
@@ -502,7 +511,7 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
         if (rr == 0) { ctx->launches++; return S2PB_OK; }
         if (rr != -2) return fail(S2PB_ERR_CUDA, "chunked aggregation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    int r = agg_launch(LPL, tsgm, P, ctx->sm_count, st);
+    int r = agg_launch(LPL, tsgm, P, ctx->sm_count, st, ctas_per_sm);
     if (r == -2) return fail(S2PB_ERR_UNSUPPORTED, "no aggregation kernel for %d labels per lane", LPL);
     if (r != 0) return fail(S2PB_ERR_CUDA, "aggregation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ctx->launches++;
@@ -1112,8 +1121,14 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
     // ---- 8-pass MGM of both views in one persistent launch (two when the views' slabs differ in width)
     if (LPLv[0] == LPLv[1]) rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, wide[0] ? gminv : nullptr);
     else {
-        rc = launch_aggregate(ctx, s, 1, w, h, LPLv[0], p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, wide[0] ? gminv : nullptr, 0);
-        if (rc == S2PB_OK) rc = launch_aggregate(ctx, s, 1, w, h, LPLv[1], p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, wide[1] ? gminv : nullptr, 1);
+        // one launch per view, side by side: each takes one persistent CTA per SM (a chain of bands per pass limits what a single
+        // view can keep busy: alone, 8 passes fill the GPU no better than 16 do), the right view on the slot's second stream
+        CK(cudaEventRecord(s.fork, st));
+        CK(cudaStreamWaitEvent(s.stream2, s.fork, 0));
+        rc = launch_aggregate(ctx, s, 1, w, h, LPLv[0], p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, wide[0] ? gminv : nullptr, 0, 1);
+        if (rc == S2PB_OK) rc = launch_aggregate(ctx, s, 1, w, h, LPLv[1], p->P1, p->P2, p->ndir, p->tsgm, lut, s.stream2, general, wgt, wide[1] ? gminv : nullptr, 1, 1);
+        CK(cudaEventRecord(s.join, s.stream2));
+        CK(cudaStreamWaitEvent(st, s.join, 0));
     }
     if (rc != S2PB_OK) return rc;
     CK(cudaEventRecord(s.ev[3], st));
