@@ -105,6 +105,14 @@ int s2pb_mgm_weighted(s2pb_ctx *ctx, const float *im1, const float *im2, int w, 
                       int dmin, int dmax, const s2pb_mgm_params *p, const float *wl, const float *wr,
                       float *disp, float *conf, uint8_t *mask, float *disp_right);
 
+/* `mgm ... -confidence_pkrL f -confidence_pkrR g` (3rdparty/mgm_multi/main_mgm.cc:147,250-262, main_mgm_multi.cc likewise):
+ * s2pb_mgm plus the peak-ratio confidence of both views (compute_PKR_confidence, mgm_costvolume.cc:199-214: second minimum of
+ * the aggregated cost more than 2 labels away from the winner, over max(first minimum, 0.01)).  With scales >= 0 the images
+ * are those of the full-resolution ZOOM = 1 call, as in mgm_multi.  s2p itself never requests them. */
+int s2pb_mgm_pkr(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+                 const s2pb_mgm_params *p, float *disp, float *conf, uint8_t *mask, float *disp_right,
+                 float *pkr_left, float *pkr_right);
+
 /* Same, device pointers on both sides, enqueued on `stream` (a cudaStream_t
  * passed as void*, NULL = the context's own stream) and NOT synchronised when
  * timeout_ms <= 0.  `slot` selects one of the context's workspaces

@@ -356,7 +356,15 @@ struct WtaParams {
     float *S;                 // optional [npix][D] dense output (stage API / PKR), D = Dout
     int Dout;
     float *disp, *cost, *conf;
+    float *pkr;               // optional: peak-ratio confidence (compute_PKR_confidence, mgm_costvolume.cc:199-214)
 };
+
+// PKR of one pixel from its lane-distributed S: second minimum over the slots of the pixel's range more than 2 away from the
+// winner, divided by max(first minimum, 0.01) in double like the reference's `secondmin / fmax(firstmin, 0.01)`
+__device__ __forceinline__ float pkr_ratio(float secondmin, float firstmin)
+{
+    return (float)((double)secondmin / fmax((double)firstmin, 0.01));
+}
 
 __device__ __forceinline__ void vfit3(float v0, float v1, float v2, float &vmin, float &xmin)
 {   // refine.h:70-92
@@ -430,6 +438,17 @@ __device__ __forceinline__ void wta_finish(const WtaParams &P, size_t p, int lan
         const int lo = P.lo[p] - P.gmin, hi = P.hi[p] - P.gmin;
         for (int kk = lane; kk < P.Dout; kk += 32)
             P.S[p * P.Dout + kk] = (kk >= lo && kk <= hi) ? sSrow[kk] : S2PB_INF;
+    }
+    if (P.pkr != nullptr) {
+        const int lo = P.lo[p] - P.gmin, hi = P.hi[p] - P.gmin;
+        float sec = S2PB_INF;
+#pragma unroll
+        for (int e = 0; e < LPL; e++) {
+            const int kk = lane * LPL + e;
+            if (kk >= lo && kk <= hi && abs(kk - kbest) > 2) sec = fminf(sec, s[e]);
+        }
+        sec = warp_min_f32(sec);
+        if (lane == 0) P.pkr[p] = pkr_ratio(sec, m);
     }
     if (P.refine != 0 && lane == 0) {
         if (o - 1 >= P.lo[p] && o + 2 <= P.hi[p]) {
@@ -656,6 +675,15 @@ __global__ void __launch_bounds__(kWtaThreads) wta_chunked_kernel(const WtaParam
 #pragma unroll
         for (int d = 0; d < kMaxPasses; d++) confi += (confi_src[d] == kbest) ? 1 : 0;
         __syncwarp();
+        if (P.pkr != nullptr) {
+            float sec = S2PB_INF;
+            for (int e = ea; e <= eb; e++) {
+                const int kk = 32 * e + lane;
+                if (kk >= lo && kk <= hi && abs(kk - kbest) > 2) sec = fminf(sec, sS[kk]);
+            }
+            sec = warp_min_f32(sec);
+            if (lane == 0) P.pkr[p] = pkr_ratio(sec, m);
+        }
         if (P.refine != 0 && lane == 0) {
             if (kbest - 1 >= lo && kbest + 2 <= hi) {                 // o - 1 >= lo_label && o + 2 <= hi_label
                 const float v0 = sS[kbest - 1], v1 = sS[kbest], v2 = sS[kbest + 1];

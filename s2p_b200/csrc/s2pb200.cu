@@ -102,6 +102,8 @@ struct s2pb_ctx {
     int *scratch_flag = nullptr;   // pinned + mapped: device -> host one-word answers
     int *d_scratch = nullptr;      // 64 words of device memory (hull accumulators of mgm_multi)
     long long launches = 0;
+    // destination of the PKR images of s2pb_mgm_pkr (device, per view), or null: every mgm_call writes them, the last one stays
+    float *pkr_dst[2] = {nullptr, nullptr};
     // deadline of the matcher call in flight (timeout_ms counted from the API entry; has_deadline = false: none)
     std::chrono::steady_clock::time_point deadline;
     bool has_deadline = false;
@@ -585,6 +587,7 @@ static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t s
 static void fill_wta(WtaParams &P, const ViewWS &v, int ndir, int gmin, const s2pb_mgm_params *p, const float *lut, size_t npix)
 {
     memset(&P, 0, sizeof P);
+    P.pkr = nullptr;
     for (int d = 0; d < ndir; d++) P.L[d] = v.L[d];
     P.C = v.C; P.lo = v.lo; P.hi = v.hi; P.lut = lut;
     P.ndir = ndir; P.gmin = gmin; P.fix_overcount = p->fix_overcount; P.refine = p->refine;
@@ -870,6 +873,7 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
         WtaParams W;
         fill_wta(W, s.v[vi], p->ndir, gminv[vi], p, lut, npix);
         W.inv_zoom_div = (float)zoom;
+        W.pkr = ctx->pkr_dst[vi];
         rc = launch_wta(ctx, LPL, W, st, general, true);
         if (rc != S2PB_OK) return rc;
     }
@@ -1005,7 +1009,10 @@ static int mgm_multi_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const f
         ctx->launches += 2;
         L0.dminL = a; L0.dmaxL = b; L0.dminR = c; L0.dmaxR = d;
         s.arena_off = mark2;
+        float *keep[2] = {ctx->pkr_dst[0], ctx->pkr_dst[1]};          // ... and with its own img_dict: the PKR images written are the ZOOM = 1 call's
+        ctx->pkr_dst[0] = ctx->pkr_dst[1] = nullptr;
         rc = mgm_call_level(ctx, s, L0, p->subpix, p, st, false);   // fresh `param` without the weight images (main_mgm_multi.cc:207)
+        ctx->pkr_dst[0] = keep[0]; ctx->pkr_dst[1] = keep[1];
         if (rc != S2PB_OK) return rc;
     }
     float *outL = d_disp;
@@ -1136,6 +1143,7 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
     for (int vi = 0; vi < 2; vi++) {
         WtaParams W;
         fill_wta(W, s.v[vi], p->ndir, gminv[vi], p, lut, npix);
+        W.pkr = ctx->pkr_dst[vi];
         rc = launch_wta(ctx, LPLv[vi], W, st, general, wide[vi]);
         if (rc != S2PB_OK) return rc;
     }
@@ -1281,6 +1289,32 @@ extern "C" int s2pb_mgm_weighted(s2pb_ctx *ctx, const float *im1, const float *i
     }
     if (disp_right) memcpy(disp_right, s.h_dispR, npix * 4);
     return S2PB_OK;
+}
+
+// `mgm ... -confidence_pkrL f -confidence_pkrR g` (main_mgm.cc:147,250-262; mgm_multi likewise): s2pb_mgm plus the peak-ratio
+// confidence images of both views.  s2p never asks for them (s2p/block_matching.py:167-183); the matcher's option surface does.
+extern "C" int s2pb_mgm_pkr(s2pb_ctx *ctx, const float *im1, const float *im2, int w, int h, int dmin, int dmax,
+                            const s2pb_mgm_params *p, float *disp, float *conf, uint8_t *mask, float *disp_right,
+                            float *pkr_left, float *pkr_right)
+{
+    if (!ctx || !pkr_left || !pkr_right) return fail(S2PB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)w * h;
+    pool_release_all(ctx);
+    float *d0 = (float *)pool_take(ctx, npix * 4), *d1 = (float *)pool_take(ctx, npix * 4);
+    if (!d0 || !d1) { pool_release_all(ctx); return fail(S2PB_ERR_NOMEM, "cudaMalloc failed for the PKR images"); }
+    ctx->pkr_dst[0] = d0; ctx->pkr_dst[1] = d1;
+    int rc = s2pb_mgm_weighted(ctx, im1, im2, w, h, dmin, dmax, p, nullptr, nullptr, disp, conf, mask, disp_right);
+    ctx->pkr_dst[0] = ctx->pkr_dst[1] = nullptr;
+    if (rc == S2PB_OK) {
+        cudaStream_t st = ctx->slots[0].stream;
+        cudaError_t e = cudaMemcpyAsync(pkr_left, d0, npix * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pkr_right, d1, npix * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(S2PB_ERR_CUDA, "copy of the PKR images failed: %s", cudaGetErrorString(e));
+    }
+    pool_release_all(ctx);
+    return rc;
 }
 
 extern "C" int s2pb_reserve(s2pb_ctx *ctx, int nslots, int w, int h, int nlabels)

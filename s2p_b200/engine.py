@@ -70,9 +70,10 @@ class Engine:
         self.close()
 
     # ------------------------------------------------------------------ matcher
-    def mgm(self, im1, im2, dmin, dmax, params=None, want_mask=True, want_right=False, weights=None):
-        """-> dict(disp, conf, mask[, disp_right]) for one rectified pair (host arrays).
-        ``weights`` = (wl, wr): the regularity weight images of ``-wl`` / ``-wr`` (mgm_multi_lsd)."""
+    def mgm(self, im1, im2, dmin, dmax, params=None, want_mask=True, want_right=False, weights=None, want_pkr=False):
+        """-> dict(disp, conf, mask[, disp_right][, pkr_left, pkr_right]) for one rectified pair (host arrays).
+        ``weights`` = (wl, wr): the regularity weight images of ``-wl`` / ``-wr`` (mgm_multi_lsd).
+        ``want_pkr``: also the peak-ratio confidence images of ``-confidence_pkrL`` / ``-confidence_pkrR``."""
         p = params or default_params("mgm")
         im1, im2 = _f32(im1), _f32(im2)
         if im1.shape != im2.shape or im1.ndim != 2:
@@ -87,6 +88,18 @@ class Engine:
         conf = np.empty((h, w), np.float32)
         mask = np.empty((h, w), np.uint8) if want_mask else None
         right = np.empty((h, w), np.float32) if want_right else None
+        if want_pkr:
+            if weights is not None:
+                raise NotImplementedError("PKR images with regularity weights")
+            pl, pr = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+            _lib.check(self._L.s2pb_mgm_pkr(
+                self._ctx, _fp(im1), _fp(im2), w, h, int(dmin), int(dmax), ctypes.byref(p), _fp(disp), _fp(conf),
+                mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if want_mask else None,
+                _fp(right) if want_right else None, _fp(pl), _fp(pr)))
+            out = dict(disp=disp, conf=conf, mask=mask, pkr_left=pl, pkr_right=pr)
+            if want_right:
+                out["disp_right"] = right
+            return out
         _lib.check(self._L.s2pb_mgm_weighted(
             self._ctx, _fp(im1), _fp(im2), w, h, int(dmin), int(dmax), ctypes.byref(p),
             _fp(wl) if wl is not None else None, _fp(wr) if wr is not None else None, _fp(disp), _fp(conf),

@@ -369,3 +369,21 @@ def test_mgm_more_than_512_labels(engine, oracle, dmin, dmax, tsgm):
     d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params(tsgm=tsgm))
     assert same(out["disp"], d), "%d px differ" % nmismatch(out["disp"], d)
     assert same(out["conf"], c) and same(out["disp_right"], dr)
+
+
+@pytest.mark.parametrize("algo,shape,dmin,dmax,nanb,kw", [
+    ("mgm", (70, 110), -12, 12, 0.05, {}), ("mgm", (45, 200), -30, 8, 0.0, dict(tsgm=4, census_win=3)), ("mgm", (37, 640), -300, 299, 0.03, {}),
+    ("mgm_multi", (120, 160), -20, 20, 0.0, {}), ("mgm_multi", (130, 170), -14, 16, 0.06, dict(subpix=1))])
+def test_pkr_confidence(engine, oracle, algo, shape, dmin, dmax, nanb, kw):
+    """the peak-ratio confidence images of -confidence_pkrL / -confidence_pkrR (mgm_costvolume.cc:199-214), bit for bit; the oracle
+    is pinned to the reference binary's own images (tests/test_oracle.py)"""
+    from s2p_b200.engine import default_params
+    h, w = shape
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=h + w, nan_border=nanb)
+    multi = algo == "mgm_multi"
+    out = engine.mgm(ref, sec, dmin, dmax, default_params(algo, **kw), want_right=True, want_pkr=True)
+    P = oracle.mgm_multi_params(**kw) if multi else oracle.mgm_params(**kw)
+    d, c, dr, pl, pr = oracle.port.mgm_pkr(ref, sec, dmin, dmax, P, multi=multi)
+    assert same(out["disp"], d) and same(out["conf"], c) and same(out["disp_right"], dr)
+    assert same(out["pkr_left"], pl), "%d px differ" % nmismatch(out["pkr_left"], pl)
+    assert same(out["pkr_right"], pr), "%d px differ" % nmismatch(out["pkr_right"], pr)

@@ -225,3 +225,20 @@ def test_rejection_mask_port_matches_reference_programs(oracle, shape, dmin, dma
     d[:, :3] -= 7.3                   # backflow samples outside the image (getsample_0: zero outside)
     d[:, -3:] += 6.6
     assert np.array_equal(oracle.port.rejection_mask(d, ref, sec), oracle.ref_rejection_mask(d, ref, sec))
+
+
+@pytest.mark.parametrize("multi,shape,dmin,dmax,nanb,kw", [
+    (False, (40, 70), -9, 10, 0.05, {}), (False, (30, 50), -3, 4, 0.1, dict(tsgm=4, census_win=3)), (False, (33, 60), -20, 5, 0.0, dict(refine=2)),
+    (True, (110, 140), -12, 14, 0.0, {}), (True, (120, 150), -10, 9, 0.05, dict(subpix=1))])
+def test_pkr_confidence_port_matches_reference_binary(oracle, multi, shape, dmin, dmax, nanb, kw):
+    """-confidence_pkrL / -confidence_pkrR (compute_PKR_confidence, mgm_costvolume.cc:199-214) of mgm and mgm_multi; in
+    mgm_multi the images written are the ZOOM = 1 call's (the SUBPIX pass has its own `param`, main_mgm_multi.cc:207)."""
+    if not _have_ref(oracle):
+        pytest.skip("oracle/_ref/mgm not built (needs /root/reference)")
+    from s2p_b200.synth import make_pair
+    h, w = shape
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=h, nan_border=nanb)
+    P = oracle.mgm_multi_params(**kw) if multi else oracle.mgm_params(**kw)
+    r = oracle.run_ref(ref, sec, dmin, dmax, P, want_pkr=True)
+    d, c, dr, pl, pr = oracle.port.mgm_pkr(ref, sec, dmin, dmax, P, multi=multi)
+    assert same(d, r["disp"]) and same(pl, r["pkrL"]) and same(pr, r["pkrR"])
