@@ -11,6 +11,12 @@ eng = Engine(0)
 ref, sec, _ = make_pair(1024, 1024, -64, 63, seed=0)
 for _ in range(2):
     out = eng.mgm(ref, sec, -64, 63, default_params("mgm"))
+# the same tile with 5 % no-data strips: the DCT round trip of the matched image, per-view slab widths
+refn, secn, _ = make_pair(1024, 1024, -64, 63, seed=1, nan_border=0.05)
+eng.mgm(refn, secn, -64, 63, default_params("mgm"), want_pkr=True)
+# a range beyond 512 labels: the chunk-skipping kernels
+rw, sw_, _ = make_pair(64, 700, -300, 299, seed=2)
+eng.mgm(rw, sw_, -300, 299, default_params("mgm"))
 # general flavour: another distance, NCC, census with -wl / -wr weights
 wl = np.maximum(np.random.default_rng(1).uniform(0, 1, ref.shape) ** 2, 0.1).astype(np.float32)
 eng.mgm(ref, sec, -64, 63, default_params("mgm", cost="btad"))
