@@ -26,13 +26,14 @@ namespace s2pb {
 // per-image bookkeeping of the round trip, in device memory (so that nothing has to synchronise with the host)
 struct RtState {
     int nrows;       // rows that need the transform
-    int pad[3];
+    int ncols;       // columns that hold a flagged pixel in any of those rows
+    int pad[2];
 };
 
 // One block per image row: copy the row to `rt`, find rowmax, flag the pixels that the round trip may change and append
 // the row to the list when it has any.  A row of zeros returns exact zeros and is skipped.
 __global__ void rt_flag_kernel(const float *__restrict__ img, int w, int h, float *__restrict__ rt, RtState *st, int *__restrict__ rowlist,
-                               float *__restrict__ rowthr)
+                               float *__restrict__ rowthr, unsigned char *__restrict__ colflag)
 {
     const int row = blockIdx.x;
     const float *src = img + (size_t)row * w;
@@ -53,7 +54,8 @@ __global__ void rt_flag_kernel(const float *__restrict__ img, int w, int h, floa
     const float thr = rowmax * ((float)w * (1.f / 16777216.f));
     bool any = false;
     if (rowmax > 0.f)
-        for (int i = threadIdx.x; i < w; i += blockDim.x) any |= fabsf(src[i]) <= thr;
+        for (int i = threadIdx.x; i < w; i += blockDim.x)
+            if (fabsf(src[i]) <= thr) { any = true; colflag[i] = 1; }      // (every writer stores the same value)
     const int cnt = __syncthreads_or(any ? 1 : 0);
     if (threadIdx.x == 0) {
         rowthr[row] = (cnt && rowmax > 0.f) ? thr : -1.f;
@@ -146,45 +148,86 @@ __global__ void __launch_bounds__(256) dct_gemm_kernel(const double *__restrict_
     }
 }
 
-// q = 0: out[r][i] = (float)(0.5 * (sum_k T01[i][k] Y[r][k] + 0.0)) for the flagged pixels of the listed rows (the
-// antisymmetric part is identically +0: its inputs are Y[k] sin(0) = +-0).  T01t is the TRANSPOSED table [k][i].  One block
-// per listed row (the grid covers every image row; blocks beyond the list return): the row's flagged pixels are
-// compacted into a list first, so that the few of them -- a no-data margin is a few percent of a row -- share one pass, and
-// each thread then runs its pixel's sequential sum with 16 table loads in flight.
-__global__ void __launch_bounds__(256) rt_inverse_kernel(const double *__restrict__ T01t, const double *__restrict__ Y, int n,
-                                                         const RtState *st, const int *__restrict__ rowlist,
-                                                         const float *__restrict__ rowthr, const float *__restrict__ img, float *__restrict__ rt)
+// the columns that hold a flagged pixel, compacted (one block; the order is irrelevant)
+__global__ void rt_collist_kernel(const unsigned char *__restrict__ colflag, int w, RtState *st, int *__restrict__ collist)
 {
-    extern __shared__ double ys[];     // [n] doubles, then the list of flagged columns [n] ints
-    int *list = reinterpret_cast<int *>(ys + n);
     __shared__ int count;
-    const int nrows = st->nrows;
-    for (int rr = blockIdx.x; rr < nrows; rr += gridDim.x) {
-        const int row = rowlist[rr];
-        const float thr = rowthr[row];
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < w; i += blockDim.x)
+        if (colflag[i]) collist[atomicAdd(&count, 1)] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) st->ncols = count;
+}
+
+// q = 0, inverse: rt[r][i] = (float)(0.5 * (sum_k T01[i][k] Y[r][k] + 0.0)) for the FLAGGED pixels of the listed rows (the
+// antisymmetric part is identically +0: its inputs are Y[k] sin(0) = +-0).  The same tiled product as dct_gemm_kernel, over
+// the listed rows x the listed columns only -- a no-data margin is a few percent of the columns, so the inverse costs a few
+// percent of the forward transform; with a ragged mask the column list grows towards the full width and the cost towards
+// that of the forward one.  T01 is [n][n] row-major (output pixel, coefficient).
+__global__ void __launch_bounds__(256) rt_inverse_gemm_kernel(const double *__restrict__ T01, const double *__restrict__ Y, int n,
+                                                              const RtState *st, const int *__restrict__ rowlist, const int *__restrict__ collist,
+                                                              const float *__restrict__ rowthr, const float *__restrict__ img, float *__restrict__ rt)
+{
+    constexpr int TO = 64, TR = 32, TK = 16, QA = 4, QB = 2;
+    __shared__ double Ts[TK][TO + 2];
+    __shared__ double Xs[TK][TR + 2];
+    __shared__ int rows_s[TR], cols_s[TO];
+    const int nrows = st->nrows, ncols = st->ncols;
+    const int otiles = (ncols + TO - 1) / TO, rtiles = (nrows + TR - 1) / TR;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    for (int item = blockIdx.x; item < otiles * rtiles; item += gridDim.x) {
+        const int o0 = (item % otiles) * TO, r0 = (item / otiles) * TR;
         __syncthreads();
-        if (threadIdx.x == 0) count = 0;
-        __syncthreads();
-        for (int k = threadIdx.x; k < n; k += blockDim.x) {
-            ys[k] = Y[(size_t)row * n + k];
-            if (fabsf(img[(size_t)row * n + k]) <= thr) list[atomicAdd(&count, 1)] = k;
-        }
-        __syncthreads();
-        const int m = count;
-        for (int q = threadIdx.x; q < m; q += blockDim.x) {
-            const int i = list[q];
-            double acc = 0.0;
-            const double *t = T01t + i;
-            int k = 0;
-            for (; k + 16 <= n; k += 16) {
-                double c[16];
+        if (threadIdx.x < TR) rows_s[threadIdx.x] = (r0 + (int)threadIdx.x < nrows) ? rowlist[r0 + threadIdx.x] : -1;
+        else if (threadIdx.x < TR + TO) { const int q = threadIdx.x - TR; cols_s[q] = (o0 + q < ncols) ? collist[o0 + q] : -1; }
+        double acc[QA][QB];
 #pragma unroll
-                for (int u = 0; u < 16; u++) c[u] = __ldg(t + (size_t)(k + u) * n);
+        for (int a = 0; a < QA; a++)
 #pragma unroll
-                for (int u = 0; u < 16; u++) acc = __dadd_rn(acc, __dmul_rn(c[u], ys[k + u]));
+            for (int b = 0; b < QB; b++) acc[a][b] = 0.0;
+        for (int k0 = 0; k0 < n; k0 += TK) {
+            __syncthreads();
+            {
+                const int col = cols_s[threadIdx.x >> 2], kk = 4 * (threadIdx.x & 3);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int k = k0 + kk + q;
+                    Ts[kk + q][threadIdx.x >> 2] = (col >= 0 && k < n) ? T01[(size_t)col * n + k] : 0.0;
+                }
+                const int row = rows_s[threadIdx.x >> 3], kx = 2 * (threadIdx.x & 7);
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int k = k0 + kx + q;
+                    Xs[kx + q][threadIdx.x >> 3] = (row >= 0 && k < n) ? Y[(size_t)row * n + k] : 0.0;
+                }
             }
-            for (; k < n; k++) acc = __dadd_rn(acc, __dmul_rn(__ldg(t + (size_t)k * n), ys[k]));
-            rt[(size_t)row * n + i] = (float)__dmul_rn(0.5, __dadd_rn(acc, 0.0));
+            __syncthreads();
+            const int kmax = (n - k0 < TK) ? n - k0 : TK;
+            for (int kk = 0; kk < kmax; kk++) {
+                double a[QA], b[QB];
+#pragma unroll
+                for (int q = 0; q < QA; q++) a[q] = Ts[kk][tx + 16 * q];
+#pragma unroll
+                for (int q = 0; q < QB; q++) b[q] = Xs[kk][ty + 16 * q];
+#pragma unroll
+                for (int qa = 0; qa < QA; qa++)
+#pragma unroll
+                    for (int qb = 0; qb < QB; qb++) acc[qa][qb] = __dadd_rn(acc[qa][qb], __dmul_rn(a[qa], b[qb]));
+            }
+        }
+#pragma unroll
+        for (int qb = 0; qb < QB; qb++) {
+            const int row = rows_s[ty + 16 * qb];
+            if (row < 0) continue;
+            const float thr = rowthr[row];
+#pragma unroll
+            for (int qa = 0; qa < QA; qa++) {
+                const int col = cols_s[tx + 16 * qa];
+                if (col < 0) continue;
+                const size_t p = (size_t)row * n + col;
+                if (fabsf(img[p]) <= thr) rt[p] = (float)__dmul_rn(0.5, __dadd_rn(acc[qa][qb], 0.0));
+            }
         }
     }
 }

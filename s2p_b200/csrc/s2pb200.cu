@@ -108,7 +108,7 @@ struct s2pb_ctx {
     std::chrono::steady_clock::time_point deadline;
     bool has_deadline = false;
     // DCT coefficient tables of the matched image's round trip, one entry per image width (dct_tables)
-    struct DctTab { int n; double *T10, *T01t, *T01, *TR01, *mc, *ms; };
+    struct DctTab { int n; double *T10, *T01, *TR01, *mc, *ms; };
     std::vector<DctTab> dct;
     // scratch pool of the warp / stage entry points: device buffers are kept between calls
     struct PoolBuf { void *p; size_t bytes; bool used; };
@@ -158,7 +158,7 @@ static int slot_layout(Slot &s, int w, int h, int DP, int ndir, int cbytes, bool
         o = take(npix * 8); if (allocate) v.census = (uint64_t *)(b + o);
         o = take(npix * 4); if (allocate) v.rt = (float *)(b + o);
         o = take(npix * 8); if (allocate) v.census_rt = (uint64_t *)(b + o);
-        o = take((size_t)h * 4); if (allocate) v.rowlist = (int *)(b + o);
+        o = take(((size_t)h + w) * 4 + w + 16); if (allocate) v.rowlist = (int *)(b + o);      // rows, then columns, then column flags
         o = take((size_t)h * 4); if (allocate) v.rowthr = (float *)(b + o);
         o = take(256); if (allocate) v.rtstate = (RtState *)(b + o);
         o = take(npix * DP * cbytes); if (allocate) v.C = (void *)(b + o);
@@ -307,7 +307,7 @@ extern "C" void s2pb_destroy(s2pb_ctx *ctx)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (auto &b : ctx->pool) cudaFree(b.p);
-    for (auto &t : ctx->dct) for (double *q : {t.T10, t.T01t, t.T01, t.TR01, t.mc, t.ms}) if (q) cudaFree(q);
+    for (auto &t : ctx->dct) for (double *q : {t.T10, t.T01, t.TR01, t.mc, t.ms}) if (q) cudaFree(q);
     if (ctx->abort_flag) cudaFreeHost(ctx->abort_flag);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     delete ctx;
@@ -609,7 +609,7 @@ static int dct_tables(s2pb_ctx *ctx, int n, bool half, const s2pb_ctx::DctTab **
     if (n > 8192) return fail(S2PB_ERR_UNSUPPORTED, "tiles wider than 8192 px are not supported (DCT tables of %d x %d doubles)", n, n);
     s2pb_ctx::DctTab *t = nullptr;
     for (auto &e : ctx->dct) if (e.n == n) t = &e;
-    if (!t) { ctx->dct.push_back({n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}); t = &ctx->dct.back(); }
+    if (!t) { ctx->dct.push_back({n, nullptr, nullptr, nullptr, nullptr, nullptr}); t = &ctx->dct.back(); }
     const double pi = 3.14159265358979323846264338327950288;
     const size_t nn = (size_t)n * n;
     std::vector<double> h;
@@ -626,17 +626,14 @@ static int dct_tables(s2pb_ctx *ctx, int n, bool half, const s2pb_ctx::DctTab **
             for (int j = 0; j < n; j++) h[(size_t)k * n + j] = 2.0 * cos(pi * (j + 0.5) * k / n);
         if ((rc = upload(&t->T10, nn)) != S2PB_OK) return rc;
     }
-    if (!half && !t->T01t) {     // transposed: [k][i]
-        h.resize(nn);
-        for (int k = 0; k < n; k++)
-            for (int i = 0; i < n; i++) h[(size_t)k * n + i] = (k == 0) ? 1.0 : 2.0 * cos(pi * k * (i + 0.5) / n);
-        if ((rc = upload(&t->T01t, nn)) != S2PB_OK) return rc;
-    }
-    if (half && !t->T01) {
+    if (!t->T01) {
         h.resize(nn);
         for (int i = 0; i < n; i++)
             for (int k = 0; k < n; k++) h[(size_t)i * n + k] = (k == 0) ? 1.0 : 2.0 * cos(pi * k * (i + 0.5) / n);
         if ((rc = upload(&t->T01, nn)) != S2PB_OK) return rc;
+    }
+    if (half && !t->TR01) {
+        h.resize(nn);
         for (int i = 0; i < n; i++)
             for (int k = 0; k < n; k++) h[(size_t)i * n + k] = (k == n - 1) ? ((i & 1) ? -1.0 : 1.0) : 2.0 * sin(pi * (k + 1) * (i + 0.5) / n);
         if ((rc = upload(&t->TR01, nn)) != S2PB_OK) return rc;
@@ -652,21 +649,23 @@ static int dct_tables(s2pb_ctx *ctx, int n, bool half, const s2pb_ctx::DctTab **
     return S2PB_OK;
 }
 
-// rt = shift(img, 0) of the reference: see dct_kernels.cuh.  Asynchronous; when no row needs it the three kernels return
-// at once.  Y: [h][w] doubles of scratch.
+// rt = shift(img, 0) of the reference: see dct_kernels.cuh.  Asynchronous; when no row needs it the kernels return at once.
+// Y: [h][w] doubles of scratch.  rowlist: room for h + w ints and w bytes (row list, column list, column flags).
 static int round_trip_zero(s2pb_ctx *ctx, const float *img, int w, int h, float *rt, RtState *state, int *rowlist, float *rowthr,
                            double *Y, cudaStream_t st)
 {
+    int *collist = rowlist + h;
+    unsigned char *colflag = reinterpret_cast<unsigned char *>(collist + w);
     const s2pb_ctx::DctTab *t;
     int rc = dct_tables(ctx, w, false, &t);
     if (rc != S2PB_OK) return rc;
-    static bool configured = false;
-    if (!configured) { CK(cudaFuncSetAttribute(rt_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12)); configured = true; }
     CK(cudaMemsetAsync(state, 0, sizeof(RtState), st));
-    rt_flag_kernel<<<h, 256, 0, st>>>(img, w, h, rt, state, rowlist, rowthr);
+    CK(cudaMemsetAsync(colflag, 0, (size_t)w, st));
+    rt_flag_kernel<<<h, 256, 0, st>>>(img, w, h, rt, state, rowlist, rowthr, colflag);
+    rt_collist_kernel<<<1, 1024, 0, st>>>(colflag, w, state, collist);
     dct_gemm_kernel<float, true><<<ctx->sm_count * 4, 256, 0, st>>>(t->T10, img, w, h, state, rowlist, Y, nullptr, nullptr, nullptr);
-    rt_inverse_kernel<<<h, 256, (size_t)w * 12, st>>>(t->T01t, Y, w, state, rowlist, rowthr, img, rt);
-    ctx->launches += 3;
+    rt_inverse_gemm_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(t->T01, Y, w, state, rowlist, collist, rowthr, img, rt);
+    ctx->launches += 4;
     CK(cudaGetLastError());
     return S2PB_OK;
 }
@@ -776,7 +775,7 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
     float *rt[2]; uint64_t *cen_rt[2]; int *rowlist[2]; float *rowthr[2]; RtState *rtstate[2];
     for (int vi = 0; vi < 2; vi++) {
         rt[vi] = arena_take<float>(s, npix); cen_rt[vi] = arena_take<uint64_t>(s, npix);
-        rowlist[vi] = arena_take<int>(s, h); rowthr[vi] = arena_take<float>(s, h); rtstate[vi] = arena_take<RtState>(s, 1);
+        rowlist[vi] = arena_take<int>(s, (size_t)h + w + w / 4 + 4); rowthr[vi] = arena_take<float>(s, h); rtstate[vi] = arena_take<RtState>(s, 1);
     }
     double *dscratch = arena_take<double>(s, npix * (zoom == 2 ? 4 : 1));
     if (!dscratch) return fail(S2PB_ERR_NOMEM, "pyramid arena exhausted");
@@ -1408,9 +1407,11 @@ struct DevBuf {
 static int stage_round_trip(s2pb_ctx *ctx, DevBuf &dv, int w, int h, cudaStream_t st, DevBuf &rt, DevBuf &aux, DevBuf &Y)
 {
     size_t npix = (size_t)w * h;
-    ALLOC(rt, npix * 4); ALLOC(aux, (size_t)h * 8 + 256); ALLOC(Y, npix * 8);
-    int rc = round_trip_zero(ctx, dv.as<float>(), w, h, rt.as<float>(), (RtState *)(aux.as<char>() + (size_t)h * 8), aux.as<int>(),
-                             (float *)(aux.as<char>() + (size_t)h * 4), Y.as<double>(), st);
+    // aux: row list [h] + column list [w] + column flags [w bytes], then the per-row thresholds [h], then the state
+    const size_t lists = ((size_t)h + w) * 4 + ((size_t)w + 15) / 16 * 16;
+    ALLOC(rt, npix * 4); ALLOC(aux, lists + (size_t)h * 4 + 256); ALLOC(Y, npix * 8);
+    int rc = round_trip_zero(ctx, dv.as<float>(), w, h, rt.as<float>(), (RtState *)(aux.as<char>() + lists + (size_t)h * 4), aux.as<int>(),
+                             (float *)(aux.as<char>() + lists), Y.as<double>(), st);
     if (rc != S2PB_OK) return rc;
     void *t = dv.p; dv.p = rt.p; rt.p = t;
     return S2PB_OK;

@@ -158,14 +158,17 @@ class Engine:
         return int(self._L.s2pb_kernel_launches(self._ctx))
 
     # ------------------------------------------------------------------ rectification warp
-    def homography(self, src, H, w, h):
+    def homography(self, src, H, w, h, out=None):
         """out(x) = src(H^-1 x) on [0,w] x [0,h]: what `homography im -h "..." out w h` computes
         (s2p/common.py:159-180), order-5 B-spline with the reference's anti-aliasing rule."""
         src = _f32(src)
         if src.ndim != 2:
             raise ValueError("src must be a 2-D array")
         Hm = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(9))
-        out = np.empty((int(h), int(w)), np.float32)
+        if out is None:
+            out = np.empty((int(h), int(w)), np.float32)
+        elif out.shape != (int(h), int(w)) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape (h, w)")     # e.g. a page-locked buffer: DMA'd directly
         _lib.check(self._L.s2pb_homography(self._ctx, _fp(src), src.shape[1], src.shape[0],
                                            Hm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _fp(out), int(w), int(h)))
         return out

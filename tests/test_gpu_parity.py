@@ -387,3 +387,21 @@ def test_pkr_confidence(engine, oracle, algo, shape, dmin, dmax, nanb, kw):
     assert same(out["disp"], d) and same(out["conf"], c) and same(out["disp_right"], dr)
     assert same(out["pkr_left"], pl), "%d px differ" % nmismatch(out["pkr_left"], pl)
     assert same(out["pkr_right"], pr), "%d px differ" % nmismatch(out["pkr_right"], pr)
+
+
+def test_nodata_with_a_ragged_mask(engine, oracle):
+    """No-data regions as a real rectified tile has them: a rotated footprint, so that every row loses another set of columns (the
+    column list of the inverse DCT grows to most of the width), plus isolated exact zeros."""
+    from s2p_b200.engine import default_params
+    h, w, dmin, dmax = 96, 180, -14, 13
+    ref, sec, _ = make_pair(h, w, dmin, dmax, seed=21)
+    yy, xx = np.mgrid[0:h, 0:w]
+    ref[xx + 2 * yy < 60] = np.nan
+    ref[xx - yy > 150] = np.nan
+    sec[3 * xx + yy < 70] = np.nan
+    sec[xx + yy > 230] = np.nan
+    sec[40:44, 90:95] = 0.0
+    out = engine.mgm(ref, sec, dmin, dmax, default_params("mgm"), want_right=True)
+    d, c, dr = oracle.port.mgm(ref, sec, dmin, dmax, oracle.mgm_params())
+    assert same(out["disp"], d), "%d px differ" % nmismatch(out["disp"], d)
+    assert same(out["conf"], c) and same(out["disp_right"], dr)
