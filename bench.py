@@ -383,6 +383,7 @@ def run_ours(a, rank, world, local_rank):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "traffic": traffic, "traffic_source": traffic_src,
+                "frac_of_peak_on_real_traffic": (traffic / (agg * 1e-3) / 1e9 / peak) if traffic else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": agg,
                 "tile_ms_serial": float(np.mean(tot_ms[1:])), "stage_ms": stage,
                 "stage_ms_overlapped": overlapped, "how": "serial single-tile launches after the timed region, CUDA events recorded by the library on the launching stream"}
