@@ -25,7 +25,7 @@ for it in range(N):
     multi = rng.random() < 0.3
     h, w = (int(rng.integers(101, 150)), int(rng.integers(101, 200))) if multi else (int(rng.integers(2, 70)), int(rng.integers(2, 300)))
     dmin = int(rng.integers(-200, 50))
-    dmax = dmin + int(rng.integers(1, min(480, max(2, 3 * w))))
+    dmax = dmin + int(rng.integers(1, min(700 if it % 7 == 0 else 480, max(2, 3 * w))))      # every 7th case may exceed 512 labels
     kw = dict(ndir=int(rng.choice([2, 4, 8])), tsgm=int(rng.integers(1, 5)), census_win=int(rng.choice([3, 5, 7])),
               P1=float(rng.choice([8.0, 12.0, 5.5])), P2=float(rng.choice([32.0, 48.0, 41.0])), median=int(rng.integers(0, 3)),
               lr_mode=int(rng.integers(0, 2)), refine=int(rng.choice([0, 1, 1, 2])), cost=int(rng.choice([0, 0, 0, 1, 2, 3, 4, 5])),
@@ -55,11 +55,7 @@ for it in range(N):
         print(it, "engine refused:", e, (h, w), dmin, dmax, kw, flush=True)
         continue
     n = (differ(out["disp"], d), differ(out["conf"], c), differ(out["disp_right"], dr))
-    if multi and kw["subpix"] == 2:      # half-pixel pass: held to the contract's tolerance
-        both = np.isfinite(d) & np.isfinite(out["disp"])
-        ok = (np.isnan(d) != np.isnan(out["disp"])).mean() < 2e-3 and (np.abs(d[both] - out["disp"][both]) > 0.25).mean() < 2e-3 and n[1] == 0
-    else:
-        ok = not any(n)
+    ok = not any(n)                       # bit-exact everywhere, the half-pixel pass of mgm_multi included (round 2)
     if not ok:
         bad += 1
     if any(n):
