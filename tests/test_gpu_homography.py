@@ -154,3 +154,43 @@ def test_fused_rectify_and_match_equals_the_file_path(engine, tmp_path):
                                 a, b, H1, H2, w, h, algo, -41, 30)
         for name in ("rectified_ref.tif", "rectified_sec.tif", "rectified_disp.tif", "rectified_disp_confidence.tif", "rectified_mask.png"):
             assert np.array_equal(rio.read_band(p(d1, name)), rio.read_band(p(d2, name)), equal_nan=True), (algo, name)
+
+
+def test_rectify_pair_and_match_with_the_reference_host_algebra(engine, tmp_path, monkeypatch):
+    """rectification.rectify_pair_and_match lets the reference's rectify_pair do its host algebra, intercepts its two
+    image_apply_homography calls and runs warps + matcher in one device call.  s2p is not importable here (rasterio, rpcm), so a
+    stand-in module with rectify_pair's contract -- compute H1, H2, the range, then call common.image_apply_homography twice,
+    s2p/rectification.py:367-382 -- takes its place; the files must equal those of the two-step drop-ins."""
+    import sys
+    import types
+    from s2p_b200 import block_matching as bm, common, rasterio_compat as rio, rectification
+    z, _, _ = _real_pair()
+    a, b = str(tmp_path / "img_01.tif"), str(tmp_path / "img_02.tif")
+    rio.write_float_tiff(a, z["crop1"].astype(np.float32))
+    rio.write_float_tiff(b, z["crop2"].astype(np.float32))
+    comp = lambda Hm, xy: np.asarray(Hm, np.float64) @ np.array([[1, 0, xy[0]], [0, 1, xy[1]], [0, 0, 1.0]])
+    H1, H2 = comp(z["H1"], z["xy1"]), comp(z["H2"], z["xy2"])
+    h, w = z["rectified_ref"].shape
+    fake_common = types.ModuleType("s2p.common")
+    fake_common.image_apply_homography = common.image_apply_homography
+    fake_rect = types.ModuleType("s2p.rectification")
+
+    def rectify_pair(im1, im2, rpc1, rpc2, x, y, ww, hh, out1, out2, A=None, sift_matches=None, method="rpc", hmargin=0, vmargin=0):
+        fake_common.image_apply_homography(out1, im1, H1, w, h)
+        fake_common.image_apply_homography(out2, im2, H2, w, h)
+        return H1, H2, -41.0, 30.0
+    fake_rect.rectify_pair = rectify_pair
+    pkg = types.ModuleType("s2p")
+    pkg.common, pkg.rectification = fake_common, fake_rect
+    for name, mod in (("s2p", pkg), ("s2p.common", fake_common), ("s2p.rectification", fake_rect)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    d1, d2 = tmp_path / "two_step", tmp_path / "fused"
+    d1.mkdir(); d2.mkdir()
+    p = lambda d, n: str(d / n)
+    rectify_pair(a, b, None, None, 0, 0, w, h, p(d1, "rectified_ref.tif"), p(d1, "rectified_sec.tif"))
+    bm.compute_disparity_map(p(d1, "rectified_ref.tif"), p(d1, "rectified_sec.tif"), p(d1, "rectified_disp.tif"), p(d1, "rectified_mask.png"), "mgm", -41.0, 30.0)
+    ret = rectification.rectify_pair_and_match(a, b, None, None, 0, 0, w, h, p(d2, "rectified_ref.tif"), p(d2, "rectified_sec.tif"),
+                                               p(d2, "rectified_disp.tif"), p(d2, "rectified_mask.png"), "mgm")
+    assert ret[2:] == (-41.0, 30.0) and fake_common.image_apply_homography is common.image_apply_homography      # patch restored
+    for name in ("rectified_ref.tif", "rectified_sec.tif", "rectified_disp.tif", "rectified_disp_confidence.tif", "rectified_mask.png"):
+        assert np.array_equal(rio.read_band(p(d1, name)), rio.read_band(p(d2, name)), equal_nan=True), name
