@@ -57,14 +57,10 @@ template <int LPL> struct SyncCfg {
     static constexpr bool sync2 = S2PB_SYNC2 && LPL > 4 && LPL <= 8;
     static constexpr int kRing = sync2 ? 8 : 4;      // ring slots per compute warp for handing vectors to the next warp
 };
+// The last add of each scanline (C + sum) as a scalar FADD instead of half of an FADD2: measured on B200 (second A/B of round 2,
+// profiles/r02_ab_variants.txt) 3.52 -> 3.40 ms per C2 launch, bit-identical (the same correctly rounded add).
 #ifndef S2PB_SCALAR_FINAL_ADD
-#define S2PB_SCALAR_FINAL_ADD 0
-#endif
-// Running cursors as 32-bit pixel indices instead of 64-bit pointers: an address is then ONE IMAD.WIDE (pixel x bytes-per-pixel +
-// loop-invariant base) straight into the aligned register pair the memory instruction needs, where a 64-bit cursor costs a
-// two-instruction add per step plus two moves into such a pair (image pixels always fit 31 bits, volumes do not)
-#ifndef S2PB_PIXEL_CURSORS
-#define S2PB_PIXEL_CURSORS 0
+#define S2PB_SCALAR_FINAL_ADD 1
 #endif
 #ifndef S2PB_PUBLISH
 #define S2PB_PUBLISH 8        // (a knob for A/B builds: fewer publications = fewer ld.acquire polls by the next band)
@@ -428,14 +424,8 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
     // ---- staging cursors.  Costs: lanes 0-15 copy scanline A, lanes 16-31 scanline B, 16 bytes each.
     const int rsel = lane >> 4, q16 = lane & 15;
     const bool live_st = rsel ? liveB : liveA;
-#if S2PB_PIXEL_CURSORS
-    const char *const cbase = reinterpret_cast<const char *>(pd.C) + 16 * q16;
-    int cpix = (int)(rowbaseA + (long long)rsel * pd.strideS);
-    const int pstep = (int)strideI;
-#else
     const char *csrc = reinterpret_cast<const char *>(pd.C) + (rowbaseA + (long long)rsel * pd.strideS) * CB + 16 * q16;
     const long long cstep = strideI * CB;
-#endif
     const unsigned cdst = smem_s + (unsigned)SM::cst_off + (unsigned)((2 * k + rsel) * kStage * CB + 16 * q16);
     const float *wsrc = weighted ? pd.W + rowbaseA + (long long)rsel * pd.strideS : nullptr;
     const unsigned wdst = smem_s + (unsigned)SM::wst_off + (unsigned)((2 * k + rsel) * kStage * 4);
@@ -454,16 +444,9 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         if (live_st && jc < nI) {
             const unsigned d = cdst + (unsigned)((jc & (kStage - 1)) * CB);
 #pragma unroll
-#if S2PB_PIXEL_CURSORS
-            const char *csrc = cbase + (long long)cpix * CB;
-#endif
             for (int q = 0; q < (CH + 15) / 16; q++)
                 if (CH % 16 == 0 || q16 + 16 * q < CH) cp_async16_s(d + 256 * q, csrc + 256 * q);
-#if S2PB_PIXEL_CURSORS
-            cpix += pstep;
-#else
             csrc += cstep;
-#endif
             if (weighted) {
                 if (q16 == 0) cp_async4_s(wdst + (unsigned)((jc & (kStage - 1)) * 4), wsrc);
                 wsrc += strideI;
@@ -491,14 +474,8 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
 
     // ---- global output cursors
     const long long lstep = strideI * DP;                    // floats per pixel step along the scanline
-#if S2PB_PIXEL_CURSORS
-    float *const lbase = pd.L + lane * LPL;
-    int opixA = (int)rowbaseA, opixB = (int)(rowbaseA + pd.strideS);
-    const int ostep = (int)strideI;
-#else
     float *outA = pd.L + rowbaseA * DP + lane * LPL;
     float *outB = outA + (long long)pd.strideS * DP;
-#endif
     float *lminB = pd.Lmin + rowbaseA + pd.strideS;          // only the band's last scanline publishes its minima
 
     auto fetch_prev = [&](int j, NbVec<LPL> &dst) {
@@ -649,13 +626,8 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
                 for (int e = 0; e < LPL; e++) hNew.v[e] = LA[e];
                 hNew.m = mAm;
                 fill_edges<LPL>(hNew, lane);
-#if S2PB_PIXEL_CURSORS
-                st_vec_out<LPL>(lbase + (long long)opixA * DP, LA);
-                opixA += ostep;
-#else
                 st_vec_out<LPL>(outA, LA);
                 outA += lstep;
-#endif
             }
             if (actB) {
 #pragma unroll
@@ -663,13 +635,8 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
                 wAB.m = mBm;
                 if (useA) fill_edges<LPL>(wAB, lane);
                 if (usePrev) st_vec<LPL>(myring + (iB & (kRing - 1)) * DP, LB);
-#if S2PB_PIXEL_CURSORS
-                st_vec_out<LPL>(lbase + (long long)opixB * DP, LB);
-                opixB += ostep;
-#else
                 st_vec_out<LPL>(outB, LB);
                 outB += lstep;
-#endif
                 if (lane == 0 && usePrev) myringm[iB & (kRing - 1)] = mBm;
                 if (publish) {
                     if (lane == 0) *lminB = mBm;
