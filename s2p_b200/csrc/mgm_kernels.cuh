@@ -286,7 +286,7 @@ __global__ void unpad_cost_kernel(const float *__restrict__ C, size_t npix, int 
     Cout[i] = C[p * DP + k];
 }
 
-// EXPERIMENTAL companion of agg_chunked.cuh (S2PB_CHUNKED=1): the census cost volume written only on the 32-slot
+// Companion of agg_chunked.cuh (slabs wider than 512 slots; S2PB_CHUNKED=1 for a measurement on narrower ones): the census cost volume written only on the 32-slot
 // chunks [ea, eb] that hold a pixel's label range (slot 32*e + lane); the chunk-skipping aggregation and WTA never
 // read the others.  Same values as cost_kernel on those chunks, including +INF on the slots of an active chunk that
 // lie outside the range and the all-invalid -> 0 rule (mgm_costvolume.cc:166-171).
@@ -509,119 +509,8 @@ __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 128
     }
 }
 
-// EXPERIMENT, off by default (S2PB_WTA_BULK=1 selects it): the same kernel fed by bulk asynchronous copies
-// (cp.async.bulk + mbarrier, the TMA engine) for the hot configuration (f16 costs, up to 4 labels per lane).
-// Motivation: while tiles overlap, only ONE 128-thread CTA of the WTA kernel fits on an SM beside the two
-// aggregation CTAs of the next tile; with register-staged loads those four warps keep ~8 KB in flight per SM, a
-// quarter of what the HBM latency-bandwidth product asks for, and the kernel stretches from 1.8 to ~6 ms.  Here one
-// thread queues the nine contiguous runs of a chunk of four pixels (8 pass volumes x 2 KB + 1 KB of costs) into a
-// 3-deep ring of shared-memory stages, so ~35 KB per SM are in flight whatever the occupancy, at no register cost.
-// Measured on B200 (bit-identical results): alone 2.6 ms instead of 1.8 ms, with tiles in flight 179 instead of
-// 188 Mpix/s -- the WTA itself stretches less (8.7 vs 13.8 ms per tile) but takes more from the aggregation it
-// shares the SM with; 8-pixel stages are slower still (5.7 ms alone).  The register-staged kernel stays the default.
-constexpr int kWtaPx = 4;         // pixels per stage = warps per CTA
-constexpr int kWtaStages = 3;
-template <int LPL> struct WtaBulkSmem {
-    static constexpr int DP = 32 * LPL;
-    static constexpr size_t cost_off = (size_t)kMaxPasses * kWtaPx * DP * 4;      // [pass][px][DP] float, then [px][DP] half
-    static constexpr size_t stage_bytes = cost_off + (size_t)kWtaPx * DP * 2;
-    static constexpr size_t bytes = kWtaStages * stage_bytes;
-};
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    unsigned ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-template <int LPL>
-__global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 64) wta_bulk_kernel(const WtaParams P)
-{
-    constexpr int DP = 32 * LPL;
-    using SM = WtaBulkSmem<LPL>;
-    extern __shared__ __align__(128) unsigned char wsm[];
-    __shared__ float sS[kWtaThreads / 32][DP];
-    __shared__ __align__(8) uint64_t full[kWtaStages];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t nchunks = (P.npix + kWtaPx - 1) / kWtaPx;
-    auto issue = [&](size_t chunk, int st) {           // one thread: queue the copies of a chunk into stage st
-        const size_t p0 = chunk * kWtaPx;
-        const unsigned n = (unsigned)((P.npix - p0 < (size_t)kWtaPx) ? (P.npix - p0) : (size_t)kWtaPx);
-        unsigned char *base = wsm + (size_t)st * SM::stage_bytes;
-        const unsigned bl = n * DP * 4, bc = n * DP * 2;
-        mbar_expect_tx(&full[st], (unsigned)P.ndir * bl + bc);
-#pragma unroll
-        for (int d = 0; d < kMaxPasses; d++)
-            if (d < P.ndir) bulk_g2s(base + (size_t)d * kWtaPx * DP * 4, P.L[d] + p0 * DP, bl, &full[st]);
-        bulk_g2s(base + SM::cost_off, reinterpret_cast<const __half *>(P.C) + p0 * DP, bc, &full[st]);
-    };
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < kWtaStages; k++) mbar_init(&full[k], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < kWtaStages; k++) {
-            const size_t ch = (size_t)blockIdx.x + (size_t)k * gridDim.x;
-            if (ch < nchunks) issue(ch, k);
-        }
-    }
-    int it = 0;
-    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, it++) {
-        const int st = it % kWtaStages;
-        mbar_wait(&full[st], (unsigned)((it / kWtaStages) & 1));
-        const size_t p = chunk * kWtaPx + wib;
-        if (p < P.npix) {
-            const unsigned char *base = wsm + (size_t)st * SM::stage_bytes;
-            float s[LPL];
-            int am[kMaxPasses];
-#pragma unroll
-            for (int e = 0; e < LPL; e++) s[e] = 0.f;
-#pragma unroll
-            for (int d = 0; d < kMaxPasses; d++) {
-                am[d] = -1;
-                if (d < P.ndir) {
-                    float v[LPL];
-                    ld_vec<LPL>(reinterpret_cast<const float *>(base) + ((size_t)d * kWtaPx + wib) * DP + lane * LPL, v);
-                    am[d] = wta_add_pass<LPL>(v, lane, s);
-                }
-            }
-            float c[LPL];
-            HalfPack<LPL> cp = lds_cost<LPL>(reinterpret_cast<const __half *>(base + SM::cost_off) + (size_t)wib * DP + lane * LPL);
-#pragma unroll
-            for (int e = 0; e < LPL; e++) c[e] = cost_value(cp.h[e], P.lut);
-            wta_finish<LPL>(P, p, lane, s, am, c, sS[wib]);
-        }
-        __syncthreads();                                // every warp is done with this stage
-        if (threadIdx.x == 0) {
-            const size_t nx = chunk + (size_t)kWtaStages * gridDim.x;
-            if (nx < nchunks) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy refill
-                issue(nx, st);
-            }
-        }
-    }
-}
-
-// EXPERIMENTAL companion of agg_chunked.cuh (S2PB_CHUNKED=1, not yet run on a GPU): the same WTA for slabs whose
-// pixels use few of their 32-label chunks.  A warp owns a pixel and only reads the chunks [ea, eb] that hold its
+// Companion of agg_chunked.cuh (slabs wider than 512 slots; S2PB_CHUNKED=1 for a measurement on narrower ones): the same WTA for
+// slabs whose pixels use few of their 32-label chunks.  A warp owns a pixel and only reads the chunks [ea, eb] that hold its
 // label range (slot 32*e + lane), so a 40-label pixel of a 512-slot slab reads 2 x 128 B per pass instead of 2 KB.
 // Per lane it keeps, for every pass, the running minimum and the LAST slot attaining it, and for S the running
 // first minimum; S itself goes to shared memory for the sub-pixel fit.  Same arithmetic as wta_kernel.

@@ -196,46 +196,4 @@ __global__ void cc_filter_kernel(const float *__restrict__ in, int n, const int 
     out[i] = (r >= 0 && area[r] <= minarea) ? __int_as_float(0x7fc00000) : in[i];
 }
 
-// ---- sub-pixel row shift out(x) = in(x + q) through the DCT interpolant, double precision
-// (shear.c:28-101 with shear = 0, called by shift() with translation -q, mgm_costvolume.cc:23-43).
-// One block per row: dct[k] = (2/n) sum_j x_j cos(pi (j+1/2) k / n), then
-// out[i] = dct[0]/2 + sum_{k>=1} dct[k] cos(pi k (i + 1/2 + q) / n), evaluated as the reference's
-// sym/antisym pair 0.5*(REDFT01(dct*cos(ka)) + RODFT01(dct*sin(ka))), a = -pi q / n.
-__global__ void dct_shift_kernel(const float *__restrict__ in, float *__restrict__ out, int n, float q)
-{
-    extern __shared__ double sm[];
-    double *x = sm, *dct = sm + n, *tab = sm + 2 * n;           // tab[m] = cos(pi m / (2n)), m in [0, 4n); 7n doubles in all
-    const int row = blockIdx.x;
-    for (int m = threadIdx.x; m < 4 * n; m += blockDim.x) tab[m] = cospi((double)m / (double)(2 * n));
-    for (int j = threadIdx.x; j < n; j += blockDim.x) x[j] = (double)in[(size_t)row * n + j];
-    __syncthreads();
-    const int four_n = 4 * n;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        double acc = 0.0;
-        int idx = k % four_n, stepi = (2 * k) % four_n;          // (2j+1)k mod 4n
-        for (int j = 0; j < n; j++) {
-            acc += 2.0 * x[j] * tab[idx];
-            idx += stepi; if (idx >= four_n) idx -= four_n;
-        }
-        dct[k] = acc / n;
-    }
-    __syncthreads();
-    const double t = (double)(-q);                               // translation passed by shift(): (0., -q) as floats
-    const double a = (3.14159265358979323846 / n) * t;
-    double *ck = x, *sk = sm + 6 * n;                            // x is dead: reuse it for dct[k] cos(ka); sk = dct[k] sin(ka)
-    for (int k = threadIdx.x; k < n; k += blockDim.x) { ck[k] = dct[k] * cos(k * a); sk[k] = dct[k] * sin(k * a); }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double sym = ck[0], anti = 0.0;
-        int idx = 0; const int stepi = (2 * i + 1) % four_n;     // k(2i+1) mod 4n ; sin(theta) = cos(theta - pi/2) -> idx - n
-        for (int k = 1; k < n; k++) {
-            idx += stepi; if (idx >= four_n) idx -= four_n;
-            int sidx = idx - n; if (sidx < 0) sidx += four_n;
-            sym += 2.0 * ck[k] * tab[idx];
-            anti += 2.0 * sk[k] * tab[sidx];
-        }
-        out[(size_t)row * n + i] = (float)(0.5 * (sym + anti));
-    }
-}
-
 }  // namespace s2pb

@@ -279,13 +279,14 @@ extern "C" s2pb_ctx *s2pb_create(int device)
     }
     ctx->scratch_flag = ctx->abort_flag + 8;
     for (int i = 0; i < 16; i++) ctx->abort_flag[i] = 0;
-    cudaFuncSetAttribute(dct_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(wta_bulk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WtaBulkSmem<4>::bytes);
-    cudaFuncSetAttribute(wta_bulk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WtaBulkSmem<3>::bytes);
     if (cudaMalloc((void **)&ctx->d_scratch, 256) != cudaSuccess) { fail(S2PB_ERR_CUDA, "cudaMalloc failed"); delete ctx; return nullptr; }
     ctx->slots.resize(1);
     if (slot_init(ctx, ctx->slots[0]) != S2PB_OK) { delete ctx; return nullptr; }
-    if (agg_configure() != 0) { fail(S2PB_ERR_CUDA, "cudaFuncSetAttribute failed for the aggregation kernels"); delete ctx; return nullptr; }
+    // function attributes are per device: every context sets them for its own (not once per process)
+    if (agg_configure() != 0 || agg_chunked_configure() != 0 ||
+        cudaFuncSetAttribute(wta_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 4) != cudaSuccess) {
+        fail(S2PB_ERR_CUDA, "cudaFuncSetAttribute failed for the aggregation kernels"); delete ctx; return nullptr;
+    }
     return ctx;
 }
 
@@ -507,8 +508,6 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
         int q = 0;
         for (int vi = first_view; vi < first_view + nviews; vi++)
             for (int p = 0; p < ndir; p++, q++) { Q.lo[q] = s.v[vi].lo; Q.hi[q] = s.v[vi].hi; Q.gmin[q] = gminv[vi]; }
-        static bool configured = false;
-        if (!configured) { if (agg_chunked_configure() != 0) return fail(S2PB_ERR_CUDA, "chunked aggregation: cudaFuncSetAttribute failed"); configured = true; }
         int rr = agg_chunked_launch(tsgm, Q, ctx->sm_count, st);
         if (rr == 0) { ctx->launches++; return S2PB_OK; }
         if (rr != -2) return fail(S2PB_ERR_CUDA, "chunked aggregation launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -526,16 +525,10 @@ template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t 
     if (zoom == 2) cost_kernel<LPL, true><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
     else cost_kernel<LPL, false><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
 }
-// S2PB_WTA_BULK=1 in the environment selects the bulk-copy fed WTA kernel (an experiment that measured slower, see mgm_kernels.cuh)
-static bool wta_bulk_enabled() { static int v = -1; if (v < 0) { const char *e = getenv("S2PB_WTA_BULK"); v = e ? atoi(e) != 0 : 0; } return v != 0; }
 template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStream_t st, bool general)
 {
     if (general) wta_kernel<LPL, true><<<sm * 16, kWtaThreads, 0, st>>>(P);
-    else if (LPL <= 4 && wta_bulk_enabled()) {
-        // as many CTAs as fit an SM alone (shared memory: 3 stages of up to 17 KB each); chunks are strided over the grid
-        const int per_sm = (int)((200 * 1024) / (WtaBulkSmem<LPL>::bytes + 4096));
-        wta_bulk_kernel<LPL><<<sm * (per_sm > 8 ? 8 : per_sm), kWtaThreads, WtaBulkSmem<LPL>::bytes, st>>>(P);
-    } else wta_kernel<LPL, false><<<sm * 16, kWtaThreads, 0, st>>>(P);
+    else wta_kernel<LPL, false><<<sm * 16, kWtaThreads, 0, st>>>(P);
 }
 template <int LPL> static void launch_cost_gen_t(const CostGenParams &P, int sm, cudaStream_t st)
 {
@@ -571,8 +564,6 @@ static int launch_wta(s2pb_ctx *ctx, int LPL, const WtaParams &P, cudaStream_t s
 {
     if (ragged && !general && P.S == nullptr && chunked_wta_enabled(32 * LPL)) {  // experimental, mgm_multi levels only
         const int DP = 32 * LPL;
-        static bool configured = false;
-        if (!configured) { CK(cudaFuncSetAttribute(wta_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 4)); configured = true; }
         wta_chunked_kernel<<<ctx->sm_count * 16, kWtaThreads, (size_t)(kWtaThreads / 32) * DP * sizeof(float), st>>>(P, DP);
         CK(cudaGetLastError());
         ctx->launches++;
