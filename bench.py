@@ -478,7 +478,9 @@ def _matcher_config(ctx, algo, W, H, dmin, dmax, B, steps, nslots, nan_border=0.
     p = default_params(algo)
     pairs = [make_pair(H, W, dmin, dmax, seed=1000 + rank * B + t, nan_border=nan_border)[:2] for t in range(B)]
     multi = algo != "mgm"
-    nslots = 1 if multi else max(1, min(nslots, B))      # mgm_multi reads a label hull back per pyramid level: serial per context
+    # mgm_multi reads a label hull back at every pyramid level, so a tile's enqueue blocks its host thread: tiles go in flight from
+    # one host thread per workspace (here; s2pb_mgm_batch does the same inside the library), at most 4 (13 GiB of volumes each)
+    nslots = max(1, min(4, nslots, B)) if multi else max(1, min(nslots, B))
     if not multi:
         eng.reserve(nslots, W, H, D + (1 if nan_border > 0 else 0))
     d_ref = [torch.from_numpy(r).to(dev) for r, _ in pairs]
@@ -489,11 +491,19 @@ def _matcher_config(ctx, algo, W, H, dmin, dmax, B, steps, nslots, nan_border=0.
     main = torch.cuda.current_stream(dev)
     hint = 2 if nan_border > 0 else 0
 
+    def one_tile(t):
+        sl = t % nslots
+        eng.mgm_device(sl, d_ref[t].data_ptr(), d_sec[t].data_ptr(), W, H, dmin, dmax, p, d_out[t][0].data_ptr(), d_out[t][1].data_ptr(),
+                       d_out[t][2].data_ptr(), 0, nodata_hint=hint, stream=streams[sl].cuda_stream)
+
     def device_step():
-        for t in range(B):
-            sl = t % nslots
-            eng.mgm_device(sl, d_ref[t].data_ptr(), d_sec[t].data_ptr(), W, H, dmin, dmax, p, d_out[t][0].data_ptr(), d_out[t][1].data_ptr(),
-                           d_out[t][2].data_ptr(), 0, nodata_hint=hint, stream=streams[sl].cuda_stream)
+        if multi and nslots > 1:       # one host thread per workspace (ctypes releases the GIL during the call)
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(nslots) as ex:
+                list(ex.map(lambda sl: [one_tile(t) for t in range(sl, B, nslots)], range(nslots)))
+        else:
+            for t in range(B):
+                one_tile(t)
 
     def fork():
         ev = torch.cuda.Event(); ev.record(main)
@@ -564,7 +574,7 @@ def _matcher_config(ctx, algo, W, H, dmin, dmax, B, steps, nslots, nan_border=0.
 def extra_c3(ctx):
     """BASELINE configs[2]: 4096x4096 ROI, tile_size 512 (+ margins: 768x532), matcher mgm_multi, disp_range 256."""
     W, H, dmin, dmax = 768, 532, -128, 127
-    res, pairs = _matcher_config(ctx, "mgm_multi", W, H, dmin, dmax, B=8, steps=2, nslots=1,
+    res, pairs = _matcher_config(ctx, "mgm_multi", W, H, dmin, dmax, B=8, steps=2, nslots=4,
                                  label="BASELINE configs[2]: mgm_multi (-S 6, SUBPIX=2, REMOVESMALLCC=25, TSGM=4) on 768x532 tiles, 256 labels")
     if ctx["cpu"]:
         from oracle import oracle as O

@@ -14,7 +14,10 @@
 #include "agg_dispatch.h"
 #include "agg_chunked.cuh"
 
+#include <atomic>
 #include <chrono>
+#include <list>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -86,6 +89,7 @@ struct Slot {
     // bump arena for the pyramid of mgm_multi (images, range images, per-level results)
     char *arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
+    int *d_small = nullptr;           // 64 words of device memory of this slot's own (hull accumulators of mgm_multi)
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // the right view's aggregation when the two views' slabs differ in width (runs beside the left one)
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -101,7 +105,7 @@ struct s2pb_ctx {
     int *abort_flag = nullptr;     // pinned + mapped: the host raises it on timeout
     int *scratch_flag = nullptr;   // pinned + mapped: device -> host one-word answers
     int *d_scratch = nullptr;      // 64 words of device memory (hull accumulators of mgm_multi)
-    long long launches = 0;
+    std::atomic<long long> launches{0};   // (mgm_multi tiles of a batch are enqueued from several host threads)
     // destination of the PKR images of s2pb_mgm_pkr (device, per view), or null: every mgm_call writes them, the last one stays
     float *pkr_dst[2] = {nullptr, nullptr};
     // deadline of the matcher call in flight (timeout_ms counted from the API entry; has_deadline = false: none)
@@ -109,7 +113,8 @@ struct s2pb_ctx {
     bool has_deadline = false;
     // DCT coefficient tables of the matched image's round trip, one entry per image width (dct_tables)
     struct DctTab { int n; double *T10, *T01, *TR01, *mc, *ms; };
-    std::vector<DctTab> dct;
+    std::list<DctTab> dct;          // a list: entries stay put while other host threads hold pointers to them
+    std::mutex dct_mu;
     // scratch pool of the warp / stage entry points: device buffers are kept between calls
     struct PoolBuf { void *p; size_t bytes; bool used; };
     std::vector<PoolBuf> pool;
@@ -240,6 +245,7 @@ static int slot_init(s2pb_ctx *ctx, Slot &s)
 {
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **)&s.d_small, 256));
     CK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
     for (auto &e : s.ev) CK(cudaEventCreate(&e));
@@ -280,6 +286,7 @@ extern "C" s2pb_ctx *s2pb_create(int device)
     ctx->scratch_flag = ctx->abort_flag + 8;
     for (int i = 0; i < 16; i++) ctx->abort_flag[i] = 0;
     if (cudaMalloc((void **)&ctx->d_scratch, 256) != cudaSuccess) { fail(S2PB_ERR_CUDA, "cudaMalloc failed"); delete ctx; return nullptr; }
+    ctx->slots.reserve(64);
     ctx->slots.resize(1);
     if (slot_init(ctx, ctx->slots[0]) != S2PB_OK) { delete ctx; return nullptr; }
     // function attributes are per device: every context sets them for its own (not once per process)
@@ -299,6 +306,7 @@ extern "C" void s2pb_destroy(s2pb_ctx *ctx)
         if (s.base) cudaFree(s.base);
         if (s.arena) cudaFree(s.arena);
         if (s.io_base) cudaFree(s.io_base);
+        if (s.d_small) cudaFree(s.d_small);
         if (s.h_in[0]) cudaFreeHost(s.h_in[0]);
         for (auto &e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
@@ -331,7 +339,7 @@ extern "C" int s2pb_default_params(const char *algo, s2pb_mgm_params *p)
 }
 
 extern "C" int s2pb_num_slots(const s2pb_ctx *ctx) { return ctx ? (int)ctx->slots.size() : 0; }
-extern "C" long long s2pb_kernel_launches(const s2pb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" long long s2pb_kernel_launches(const s2pb_ctx *ctx) { return ctx ? ctx->launches.load() : 0LL; }
 
 extern "C" int s2pb_sync(s2pb_ctx *ctx)
 {
@@ -343,6 +351,10 @@ extern "C" int s2pb_sync(s2pb_ctx *ctx)
 
 static int ensure_slots(s2pb_ctx *ctx, int nslots)
 {
+    // slots may be requested from several host threads (one per workspace for mgm_multi); the vector's capacity is reserved at
+    // creation so that references to existing slots stay valid while it grows
+    if (nslots > 64) return fail(S2PB_ERR_ARG, "at most 64 workspaces per context");
+    std::lock_guard<std::mutex> lock(ctx->dct_mu);
     while ((int)ctx->slots.size() < nslots) {
         ctx->slots.emplace_back();
         int r = slot_init(ctx, ctx->slots.back());
@@ -598,6 +610,7 @@ static void fill_wta(WtaParams &P, const ViewWS &v, int ndir, int gmin, const s2
 static int dct_tables(s2pb_ctx *ctx, int n, bool half, const s2pb_ctx::DctTab **out)
 {
     if (n > 8192) return fail(S2PB_ERR_UNSUPPORTED, "tiles wider than 8192 px are not supported (DCT tables of %d x %d doubles)", n, n);
+    std::lock_guard<std::mutex> lock(ctx->dct_mu);
     s2pb_ctx::DctTab *t = nullptr;
     for (auto &e : ctx->dct) if (e.n == n) t = &e;
     if (!t) { ctx->dct.push_back({n, nullptr, nullptr, nullptr, nullptr, nullptr}); t = &ctx->dct.back(); }
@@ -771,7 +784,7 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
     double *dscratch = arena_take<double>(s, npix * (zoom == 2 ? 4 : 1));
     if (!dscratch) return fail(S2PB_ERR_NOMEM, "pyramid arena exhausted");
     // hull accumulators live in device memory (atomics on mapped host memory need PCIe atomics); copied back once
-    int *d_hull = ctx->d_scratch;
+    int *d_hull = s.d_small;
     const int hull_init[4] = {0x7fffffff, (int)0x80000000, 0x7fffffff, (int)0x80000000};
     CK(cudaMemcpyAsync(d_hull, hull_init, sizeof hull_init, cudaMemcpyHostToDevice, st));
     label_ranges_kernel<<<(n + 255) / 256, 256, 0, st>>>(L.dminL, L.dmaxL, n, (float)zoom, lo[0], hi[0], d_hull);
@@ -1038,12 +1051,15 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
     const size_t npix = (size_t)w * h;
     const int n = (int)npix;
     if (nodata_hint < 0) {     // unknown: look (costs one stream synchronisation)
-        *ctx->scratch_flag = 0;
-        has_nan_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_im2, n, ctx->scratch_flag);
+        int *flag = s.d_small + 16;      // this slot's own word (several slots may ask at once)
+        CK(cudaMemsetAsync(flag, 0, 4, st));
+        has_nan_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_im2, n, flag);
         ctx->launches++;
+        int hflag = 0;
+        CK(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
         int rs = sync_or_timeout(ctx, st);
         if (rs != S2PB_OK) return rs;
-        nodata_hint = *(volatile int *)ctx->scratch_flag ? 3 : 0;
+        nodata_hint = hflag ? 3 : 0;
     }
     int gminv[2], gmaxv[2];
     plan_labels(dmin, dmax, (nodata_hint & 2) != 0, gminv, gmaxv);
@@ -1336,8 +1352,37 @@ extern "C" int s2pb_mgm_batch(s2pb_ctx *ctx, int n, const float *const *im1, con
     CK(cudaSetDevice(ctx->device));
     const int ns = (int)ctx->slots.size();
     const size_t npix = (size_t)w * h;
-    std::vector<int> inflight(ns, -1);
     set_deadline(ctx, p->timeout_ms * (long long)(n > 0 ? n : 1));       // the per-tile timeout times the number of tiles
+    if (p->scales >= 0 && ns > 1 && n > 1) {
+        // mgm_multi reads a label hull back at every pyramid level, so a tile's enqueue blocks its host thread: one thread per
+        // workspace keeps several tiles in flight (their kernels overlap on the device, each on its slot's stream)
+        const int T = (ns < n ? ns : n) < 4 ? (ns < n ? ns : n) : 4;     // (a C3-sized tile holds 13 GiB of volumes at its widest level)
+        std::vector<int> codes(T, S2PB_OK);
+        std::vector<std::string> errs(T);
+        std::atomic<bool> stop{false};
+        std::vector<std::thread> th;
+        for (int k = 0; k < T; k++)
+            th.emplace_back([&, k]() {
+                cudaSetDevice(ctx->device);
+                Slot &s = ctx->slots[k];
+                for (int t = k; t < n && !stop.load(); t += T) {
+                    int r = mgm_host_enqueue(ctx, s, im1[t], im2[t], w, h, dmin, dmax, p, mask && mask[t], false, disp[t], conf[t],
+                                             mask ? mask[t] : nullptr);
+                    if (r == S2PB_OK) r = wait_with_timeout(ctx, s.stream);
+                    if (r != S2PB_OK) { codes[k] = r; errs[k] = g_err; stop.store(true); break; }
+                    if (!s.direct_out) {
+                        memcpy(disp[t], s.h_disp, npix * 4);
+                        memcpy(conf[t], s.h_conf, npix * 4);
+                        if (mask && mask[t]) memcpy(mask[t], s.h_mask, npix);
+                    }
+                }
+            });
+        for (auto &t : th) t.join();
+        for (int k = 0; k < T; k++)
+            if (codes[k] != S2PB_OK) { drain_all(ctx, true); g_err = errs[k]; return codes[k]; }
+        return S2PB_OK;
+    }
+    std::vector<int> inflight(ns, -1);
     auto collect = [&](int si) -> int {
         Slot &s = ctx->slots[si];
         int t = inflight[si];
