@@ -391,6 +391,23 @@ __device__ __forceinline__ void parabola3(float v0, float v1, float v2, float &v
 // mgm_core.cc:1041-1042), first strict minimum over finite S (:1044-1048), consensus (:1054-1057),
 // V-fit / parabola on S[o-1..o+1] when o-1 >= lo and o+2 <= hi (mgm_refine.h:67-84).
 
+// Which slots a lane of the WTA warp owns.  The sums are element-wise, so the WTA is free to choose: blocked (lane*LPL + e, one
+// 8-/16-byte request per lane) when LPL is a multiple of 4 or is 2, interleaved (32*e + lane, LPL 4-byte requests of 128 contiguous
+// bytes) for LPL = 3, 5, 6 -- a blocked lane stride of 12/20/24 bytes makes every request touch all of the pixel's 32-byte sectors
+// (3-5x the L2->SM traffic; wta_kernel<5> ran at 0.54 of HBM peak against 0.79-0.85 for LPL 4/8/16, profiles/r02_all_kernels.md).
+// Both enumerate a lane's slots in ascending order, which is all the first-/last-minimum rules below need.
+template <int LPL> struct WtaMap {
+    static constexpr bool interleaved = (LPL == 3 || LPL == 5 || LPL == 6);
+    static __device__ __forceinline__ int slot(int lane, int e) { return interleaved ? 32 * e + lane : lane * LPL + e; }
+};
+template <int LPL> __device__ __forceinline__ void wta_ld_pass(const float *px, int lane, float (&v)[LPL])
+{
+    if constexpr (WtaMap<LPL>::interleaved) {
+#pragma unroll
+        for (int e = 0; e < LPL; e++) v[e] = __ldcg(px + 32 * e + lane);
+    } else ld_vec_cg<LPL>(px + lane * LPL, v);
+}
+
 // one pass' vector of this pixel: add it to S, note the LAST slot attaining the pass minimum (mgm_core.cc:1015-1019)
 template <int LPL> __device__ __forceinline__ int wta_add_pass(const float (&v)[LPL], int lane, float (&s)[LPL])
 {
@@ -400,7 +417,7 @@ template <int LPL> __device__ __forceinline__ int wta_add_pass(const float (&v)[
     const float md = warp_min_f32(lm);
     int a = -1;
 #pragma unroll
-    for (int e = 0; e < LPL; e++) { if (v[e] == md) a = lane * LPL + e; s[e] += v[e]; }
+    for (int e = 0; e < LPL; e++) { if (v[e] == md) a = WtaMap<LPL>::slot(lane, e); s[e] += v[e]; }
     return __reduce_max_sync(0xffffffffu, a);
 }
 // everything after the sums: overcount fix, winner, consensus, sub-pixel fit, outputs.  sSrow: DP floats of shared memory
@@ -414,7 +431,7 @@ __device__ __forceinline__ void wta_finish(const WtaParams &P, size_t p, int lan
 #pragma unroll
     for (int e = 0; e < LPL; e++) {
         if (P.fix_overcount == 1) s[e] = fmaf(-(float)(P.ndir - 1), c[e], s[e]);
-        if (isfinite(s[e]) && best > s[e]) { best = s[e]; bidx = lane * LPL + e; }
+        if (isfinite(s[e]) && best > s[e]) { best = s[e]; bidx = WtaMap<LPL>::slot(lane, e); }
     }
     const float m = warp_min_f32(best);
     int cand = (best == m && bidx != 0x7fffffff) ? bidx : 0x7fffffff;
@@ -431,7 +448,7 @@ __device__ __forceinline__ void wta_finish(const WtaParams &P, size_t p, int lan
     if (P.S != nullptr || P.refine != 0) {
         __syncwarp();
 #pragma unroll
-        for (int e = 0; e < LPL; e++) sSrow[lane * LPL + e] = s[e];
+        for (int e = 0; e < LPL; e++) sSrow[WtaMap<LPL>::slot(lane, e)] = s[e];
         __syncwarp();
     }
     if (P.S != nullptr) {
@@ -444,7 +461,7 @@ __device__ __forceinline__ void wta_finish(const WtaParams &P, size_t p, int lan
         float sec = S2PB_INF;
 #pragma unroll
         for (int e = 0; e < LPL; e++) {
-            const int kk = lane * LPL + e;
+            const int kk = WtaMap<LPL>::slot(lane, e);
             if (kk >= lo && kk <= hi && abs(kk - kbest) > 2) sec = fminf(sec, s[e]);
         }
         sec = warp_min_f32(sec);
@@ -491,7 +508,7 @@ __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 128
             float v[4][LPL];
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                if (g + q < P.ndir) ld_vec_cg<LPL>(P.L[g + q] + p * DP + lane * LPL, v[q]);
+                if (g + q < P.ndir) wta_ld_pass<LPL>(P.L[g + q] + p * DP, lane, v[q]);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 am[g + q] = -1;
@@ -499,8 +516,12 @@ __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 128
             }
         }
         float c[LPL];
-        if constexpr (GEN) ld_vec_cg<LPL>(reinterpret_cast<const float *>(P.C) + p * DP + lane * LPL, c);
-        else {
+        if constexpr (GEN) wta_ld_pass<LPL>(reinterpret_cast<const float *>(P.C) + p * DP, lane, c);
+        else if constexpr (WtaMap<LPL>::interleaved) {
+            const unsigned short *cp = reinterpret_cast<const unsigned short *>(P.C) + p * DP + lane;
+#pragma unroll
+            for (int e = 0; e < LPL; e++) c[e] = cost_value(__ldg(cp + 32 * e), P.lut);
+        } else {
             HalfPack<LPL> cp = ld_cost<LPL>(reinterpret_cast<const __half *>(P.C) + p * DP + lane * LPL);
 #pragma unroll
             for (int e = 0; e < LPL; e++) c[e] = cost_value(cp.h[e], P.lut);
