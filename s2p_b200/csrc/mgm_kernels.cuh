@@ -423,8 +423,8 @@ template <int LPL> __device__ __forceinline__ int wta_add_pass(const float (&v)[
 // everything after the sums: overcount fix, winner, consensus, sub-pixel fit, outputs.  sSrow: DP floats of shared memory
 template <int LPL>
 __device__ __forceinline__ void wta_finish(const WtaParams &P, size_t p, int lane, float (&s)[LPL], const int (&am)[kMaxPasses],
-                                           const float (&c)[LPL], float *sSrow)
-{
+                                           const float (&c)[LPL], float *sSrow, int plo, int phi)
+{   // plo, phi: the pixel's label range, loaded by the caller ahead of the sums (off the dependent chain of the pixel)
     constexpr int DP = 32 * LPL;
     float best = S2PB_INF;
     int bidx = 0x7fffffff;
@@ -452,12 +452,12 @@ __device__ __forceinline__ void wta_finish(const WtaParams &P, size_t p, int lan
         __syncwarp();
     }
     if (P.S != nullptr) {
-        const int lo = P.lo[p] - P.gmin, hi = P.hi[p] - P.gmin;
+        const int lo = plo - P.gmin, hi = phi - P.gmin;
         for (int kk = lane; kk < P.Dout; kk += 32)
             P.S[p * P.Dout + kk] = (kk >= lo && kk <= hi) ? sSrow[kk] : S2PB_INF;
     }
     if (P.pkr != nullptr) {
-        const int lo = P.lo[p] - P.gmin, hi = P.hi[p] - P.gmin;
+        const int lo = plo - P.gmin, hi = phi - P.gmin;
         float sec = S2PB_INF;
 #pragma unroll
         for (int e = 0; e < LPL; e++) {
@@ -468,7 +468,7 @@ __device__ __forceinline__ void wta_finish(const WtaParams &P, size_t p, int lan
         if (lane == 0) P.pkr[p] = pkr_ratio(sec, m);
     }
     if (P.refine != 0 && lane == 0) {
-        if (o - 1 >= P.lo[p] && o + 2 <= P.hi[p]) {
+        if (o - 1 >= plo && o + 2 <= phi) {
             const float v0 = sSrow[kbest - 1], v1 = sSrow[kbest], v2 = sSrow[kbest + 1];
             float dx = 0.f, dxr = 0.f, ml = minL, mlr = minP;
             if (P.refine == 1) { vfit3(v0, v1, v2, ml, dx); vfit3(v2, v1, v0, mlr, dxr); }
@@ -486,11 +486,12 @@ __device__ __forceinline__ void wta_finish(const WtaParams &P, size_t p, int lan
     __syncwarp();
 }
 
-// 128-thread CTAs capped at 56 registers for LPL <= 4: one of them still fits on an SM next to the two resident
-// CTAs of the (issue-bound) aggregation kernel of the NEXT tile, so this memory-bound kernel overlaps it.
+// 128-thread CTAs capped at 64 registers for LPL <= 4: one of them still fits on an SM next to the two resident
+// CTAs of the (issue-bound) aggregation kernel of the NEXT tile (2 x 256 x 112 + 128 x 64 = the 64 K registers of an SM), so this
+// memory-bound kernel overlaps it.
 constexpr int kWtaThreads = 128;
 template <int LPL, bool GEN>
-__global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 128) wta_kernel(const WtaParams P)
+__global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 64 : 128) wta_kernel(const WtaParams P)
 {
     constexpr int DP = 32 * LPL;
     __shared__ float sS[kWtaThreads / 32][DP];
@@ -501,6 +502,13 @@ __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 128
         int am[kMaxPasses];
 #pragma unroll
         for (int e = 0; e < LPL; e++) s[e] = 0.f;
+        // the pixel's range and (f16 flavour) its costs are requested first: they are consumed last, and a warp's pixel is one
+        // dependent chain -- next to the aggregation kernel only four warps per SM run this kernel, so its rate there is
+        // 1 / chain length, and every global load that waits at the end of the chain is ~1000 cycles of it
+        const int plo = __ldg(P.lo + p), phi = __ldg(P.hi + p);
+        constexpr bool early_cost = !GEN && !WtaMap<LPL>::interleaved && LPL <= 8;      // (wider: no registers to spare)
+        HalfPack<early_cost ? LPL : 1> cpk;
+        if constexpr (early_cost) cpk = ld_cost<LPL>(reinterpret_cast<const __half *>(P.C) + p * DP + lane * LPL);
         // the passes' vectors are requested four at a time before any is consumed (memory-level parallelism
         // within the register budget that lets this kernel share an SM with the aggregation kernel)
 #pragma unroll
@@ -521,12 +529,15 @@ __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 56 : 128
             const unsigned short *cp = reinterpret_cast<const unsigned short *>(P.C) + p * DP + lane;
 #pragma unroll
             for (int e = 0; e < LPL; e++) c[e] = cost_value(__ldg(cp + 32 * e), P.lut);
+        } else if constexpr (early_cost) {
+#pragma unroll
+            for (int e = 0; e < LPL; e++) c[e] = cost_value(cpk.h[e], P.lut);
         } else {
             HalfPack<LPL> cp = ld_cost<LPL>(reinterpret_cast<const __half *>(P.C) + p * DP + lane * LPL);
 #pragma unroll
             for (int e = 0; e < LPL; e++) c[e] = cost_value(cp.h[e], P.lut);
         }
-        wta_finish<LPL>(P, p, lane, s, am, c, sS[wib]);
+        wta_finish<LPL>(P, p, lane, s, am, c, sS[wib], plo, phi);
     }
 }
 
