@@ -490,12 +490,15 @@ __device__ __forceinline__ void wta_finish(const WtaParams &P, size_t p, int lan
 // CTAs of the (issue-bound) aggregation kernel of the NEXT tile (2 x 256 x 112 + 128 x 64 = the 64 K registers of an SM), so this
 // memory-bound kernel overlaps it.
 constexpr int kWtaThreads = 128;
-template <int LPL, bool GEN>
-__global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 64 : 128) wta_kernel(const WtaParams P)
+// NDIR: the number of passes when it is known at compile time (8: every s2p configuration), 0 = read P.ndir.  With a run-time
+// count every pass sits behind its own branch and the eight (minimum -> compare -> last index) reductions of a pixel run one
+// after the other; with NDIR = 8 they are straight-line code the scheduler interleaves.
+template <int LPL, bool GEN, int NDIR>
+__device__ __forceinline__ void wta_pixels(const WtaParams &P, float *sSrow)
 {
     constexpr int DP = 32 * LPL;
-    __shared__ float sS[kWtaThreads / 32][DP];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ndir = NDIR ? NDIR : P.ndir;
+    const int lane = threadIdx.x & 31;
     size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t p = warp; p < P.npix; p += nwarps) {
         float s[LPL];
@@ -516,11 +519,11 @@ __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 64 : 128
             float v[4][LPL];
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                if (g + q < P.ndir) wta_ld_pass<LPL>(P.L[g + q] + p * DP, lane, v[q]);
+                if (g + q < ndir) wta_ld_pass<LPL>(P.L[g + q] + p * DP, lane, v[q]);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 am[g + q] = -1;
-                if (g + q < P.ndir) am[g + q] = wta_add_pass<LPL>(v[q], lane, s);
+                if (g + q < ndir) am[g + q] = wta_add_pass<LPL>(v[q], lane, s);
             }
         }
         float c[LPL];
@@ -537,8 +540,16 @@ __global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 64 : 128
 #pragma unroll
             for (int e = 0; e < LPL; e++) c[e] = cost_value(cp.h[e], P.lut);
         }
-        wta_finish<LPL>(P, p, lane, s, am, c, sS[wib], plo, phi);
+        wta_finish<LPL>(P, p, lane, s, am, c, sSrow, plo, phi);
     }
+}
+template <int LPL, bool GEN>
+__global__ void __launch_bounds__(kWtaThreads) __maxnreg__((LPL <= 4) ? 64 : 128) wta_kernel(const WtaParams P)
+{
+    __shared__ float sS[kWtaThreads / 32][32 * LPL];
+    float *sSrow = sS[threadIdx.x >> 5];
+    if (P.ndir == kMaxPasses) wta_pixels<LPL, GEN, kMaxPasses>(P, sSrow);
+    else wta_pixels<LPL, GEN, 0>(P, sSrow);
 }
 
 // Companion of agg_chunked.cuh (slabs wider than 512 slots; S2PB_CHUNKED=1 for a measurement on narrower ones): the same WTA for
