@@ -253,7 +253,11 @@ struct AggParams {
 // because pixel 0 is staged ahead of the pipeline); shallower for the widest volumes.  (16 labels per lane would
 // still fit 227 KB with 8 stages, but measured no faster: 32.7 vs 31.9 ms on the C3-like mgm_multi tile.)
 template <int LPL, bool GEN = false> struct StageCfg {
+#ifdef S2PB_STAGE          // (A/B builds: depth of the f16 flavour's pipeline for up to 12 labels per lane)
+    static constexpr int kStage = GEN ? ((LPL <= 4) ? 8 : (LPL <= 8) ? 4 : 2) : ((LPL <= 12) ? S2PB_STAGE : 2);
+#else
     static constexpr int kStage = GEN ? ((LPL <= 4) ? 8 : (LPL <= 8) ? 4 : 2) : ((LPL <= 12) ? 8 : 2);
+#endif
     static constexpr int kR0 = 2 * kStage;
 };
 
@@ -458,10 +462,12 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
         if (stage_prev) {
             if (jp < nI) {
                 int spins = 0;
+#ifndef S2PB_DIAG_NOPOLL      // timing diagnostics only (results are wrong): never wait for the previous band
                 while (avail < jp + 1) {
                     avail = ld_acquire(prev_progress);
                     if (((++spins) & 1023) == 0 && *(volatile const int *)abort_flag) break;
                 }
+#endif
                 const unsigned slot = (unsigned)(jp & (kR0 - 1));
                 warp_cp_async_s<DP * 4>(r0_s + slot * (DP * 4), psrc, lane);
                 if (lane == 0) cp_async4_s(r0m_s + slot * 4, pmsrc);
@@ -648,8 +654,12 @@ __device__ __forceinline__ void run_band(const PassDesc &pd, int band, float P1,
                 }
             }
         }
+#ifdef S2PB_DIAG_NOBAR         // timing diagnostics only (results are wrong): no CTA barrier per step
+        __syncwarp();
+#else
         if (!SYNC2 || (t & 1)) __syncthreads();
         else __syncwarp();      // the staging slot the lanes just read is overwritten by the next step's cp.async
+#endif
     };
     // a step is FAST for this warp when A is at an interior pixel with B one SKEW behind, also interior
     const bool can_fast = liveA && liveB && prevA;

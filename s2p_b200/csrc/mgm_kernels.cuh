@@ -55,7 +55,11 @@ __global__ void has_nan_kernel(const float *__restrict__ in, int n, int *flag)
 // finite, the whole range is set to 0.  Slots outside [lo,hi] stay +INF.
 // With ZOOMFACTOR = 2 (mgm_costvolume.cc:145-154) label o compares cu(x) with the census of the matched image
 // shifted by (o mod 2)/2 pixel, at column x + floor(o/2): cv = shift 0, cv1 = shift 1/2.
-template <int LPL, bool ZOOM2>
+// NARROW: the census codes fit 32 bits (3x3 and 5x5 windows: 8 and 24 bits), so one POPC on the low words does it.
+// The Hamming distance goes to f16 without a conversion instruction: the half with bits 0x6400 + v is 1024 + v exactly
+// (v < 1024), and subtracting 1024 in half2 arithmetic leaves v -- two labels per HADD2 instead of an I2F and an F2F each, which
+// share the quarter-rate pipe with POPC (that pipe, not issue, bounded the round-1 kernel: four such operations per label).
+template <int LPL, bool ZOOM2, bool NARROW>
 __global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__restrict__ cv, const uint64_t *__restrict__ cv1,
                             int w, int h,
                             const short *__restrict__ lo, const short *__restrict__ hi, int gmin, __half *__restrict__ C)
@@ -67,35 +71,38 @@ __global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__r
     for (size_t p = warp; p < npix; p += nwarps) {
         int x = (int)(p % w);
         size_t row = p - x;
-        uint64_t a = cu[p];
-        int l = lo[p], hgh = hi[p];
-        float c[LPL];
-        bool anyfinite = false;
+        const uint64_t a = cu[p];
+        const int l = lo[p], hgh = hi[p];
+        unsigned cnt[LPL];                   // Hamming distance where the label has one, else 0
+        unsigned okm = 0, inm = 0;           // bit e: label e has a distance / lies in the pixel's range
 #pragma unroll
         for (int e = 0; e < LPL; e++) {
-            int o = gmin + lane * LPL + e;
-            float v = S2PB_INF;
+            const int o = gmin + lane * LPL + e;
+            cnt[e] = 0;
             if (o >= l && o <= hgh) {
+                inm |= 1u << e;
                 int q = x + o;
                 const uint64_t *codes = cv;
                 if (ZOOM2) { q = x + (o >> 1); if (o & 1) codes = cv1; }          // floor(o/2), goodmod(o,2)
-                if (q >= 0 && q < w) { v = (float)__popcll(a ^ codes[row + q]); anyfinite = true; }
-            }
-            c[e] = v;
-        }
-        if (!__any_sync(0xffffffffu, anyfinite)) {
-#pragma unroll
-            for (int e = 0; e < LPL; e++) {
-                int o = gmin + lane * LPL + e;
-                if (o >= l && o <= hgh) c[e] = 0.f;
+                if (q >= 0 && q < w) {
+                    if constexpr (NARROW) cnt[e] = __popc((unsigned)a ^ reinterpret_cast<const unsigned *>(codes)[2 * (row + q)]);
+                    else cnt[e] = __popcll(a ^ codes[row + q]);
+                    okm |= 1u << e;
+                }
             }
         }
+        // no label of the range has a distance: the whole range is 0 (mgm_costvolume.cc:166-171); cnt is 0 there already
+        const unsigned fin = __any_sync(0xffffffffu, okm != 0) ? okm : inm;
         __half *dst = C + p * DP + lane * LPL;
         if constexpr (LPL % 2 == 0) {          // packed stores: 4, 8 or 16 bytes per lane
             unsigned wds[LPL / 2];
 #pragma unroll
-            for (int e = 0; e < LPL / 2; e++)
-                wds[e] = (unsigned)__half_as_ushort(__float2half_rn(c[2 * e])) | ((unsigned)__half_as_ushort(__float2half_rn(c[2 * e + 1])) << 16);
+            for (int e = 0; e < LPL / 2; e++) {
+                unsigned pk = 0x64006400u + (cnt[2 * e] | (cnt[2 * e + 1] << 16));
+                __half2 hv = __hsub2(*reinterpret_cast<__half2 *>(&pk), __half2half2(__ushort_as_half((unsigned short)0x6400)));
+                const unsigned m = ((fin >> (2 * e)) & 1u ? 0x0000ffffu : 0u) | ((fin >> (2 * e + 1)) & 1u ? 0xffff0000u : 0u);
+                wds[e] = (*reinterpret_cast<unsigned *>(&hv) & m) | (0x7c007c00u & ~m);
+            }
             if constexpr (LPL % 8 == 0) {
 #pragma unroll
                 for (int q = 0; q < LPL / 8; q++) reinterpret_cast<uint4 *>(dst)[q] = make_uint4(wds[4 * q], wds[4 * q + 1], wds[4 * q + 2], wds[4 * q + 3]);
@@ -108,7 +115,7 @@ __global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__r
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < LPL; e++) dst[e] = __float2half_rn(c[e]);
+            for (int e = 0; e < LPL; e++) dst[e] = (fin >> e) & 1u ? __float2half_rn((float)cnt[e]) : __ushort_as_half((unsigned short)0x7c00);
         }
     }
 }

@@ -396,6 +396,19 @@ static int sync_or_timeout(s2pb_ctx *ctx, cudaStream_t st)
     }
 }
 
+// Is another workspace's aggregation queued or running?  (ev[3] of a slot is recorded right after its aggregation; an event that
+// was never recorded reads as complete.)  A racy answer is harmless: it only picks the grid size.
+static bool other_aggregation_pending(s2pb_ctx *ctx, const Slot &me)
+{
+    const size_t n = ctx->slots.size();
+    for (size_t k = 0; k < n; k++) {
+        const Slot &o = ctx->slots[k];
+        if (&o == &me || !o.ev[3]) continue;
+        if (cudaEventQuery(o.ev[3]) == cudaErrorNotReady) return true;
+    }
+    return false;
+}
+
 // ------------------------------------------------------------------ stage launchers
 
 static dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
@@ -531,11 +544,16 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
     return S2PB_OK;
 }
 
-template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t *cv, const uint64_t *cv1, int zoom, int w, int h,
+template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t *cv, const uint64_t *cv1, int zoom, bool narrow, int w, int h,
                                              const short *lo, const short *hi, int gmin, __half *C, int sm, cudaStream_t st)
 {
-    if (zoom == 2) cost_kernel<LPL, true><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
-    else cost_kernel<LPL, false><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
+    if (zoom == 2) {
+        if (narrow) cost_kernel<LPL, true, true><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
+        else cost_kernel<LPL, true, false><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
+    } else {
+        if (narrow) cost_kernel<LPL, false, true><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
+        else cost_kernel<LPL, false, false><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
+    }
 }
 template <int LPL> static void launch_wta_t(const WtaParams &P, int sm, cudaStream_t st, bool general)
 {
@@ -556,10 +574,12 @@ template <int LPL> static void launch_cost_gen_t(const CostGenParams &P, int sm,
     default: return fail(S2PB_ERR_UNSUPPORTED, "unsupported labels-per-lane %d", LPL);     \
     }
 
-static int launch_cost(s2pb_ctx *ctx, int LPL, const uint64_t *cu, const uint64_t *cv, int w, int h, const short *lo, const short *hi,
+// census_win: the census window the codes were made with (3 and 5 leave the high word of a code zero)
+static int launch_cost(s2pb_ctx *ctx, int LPL, int census_win, const uint64_t *cu, const uint64_t *cv, int w, int h, const short *lo, const short *hi,
                        int gmin, void *C, cudaStream_t st, const uint64_t *cv1 = nullptr, int zoom = 1)
 {
-    LPL_SWITCH(LPL, launch_cost_t<K>(cu, cv, cv1, zoom, w, h, lo, hi, gmin, (__half *)C, ctx->sm_count, st));
+    const bool narrow = census_win <= 5;
+    LPL_SWITCH(LPL, launch_cost_t<K>(cu, cv, cv1, zoom, narrow, w, h, lo, hi, gmin, (__half *)C, ctx->sm_count, st));
     CK(cudaGetLastError());
     ctx->launches++;
     return S2PB_OK;
@@ -863,7 +883,7 @@ static int mgm_call_level(s2pb_ctx *ctx, Slot &s, Level &L, int zoom, const s2pb
             ctx->launches++;
             rc = cudaGetLastError() == cudaSuccess ? S2PB_OK : fail(S2PB_ERR_CUDA, "cost_chunked_kernel launch failed");
         } else {
-            rc = launch_cost(ctx, LPL, s.v[vi].census, cen_rt[1 - vi], w, h, lo[vi], hi[vi], gminv[vi], s.v[vi].C, st,
+            rc = launch_cost(ctx, LPL, p->census_win, s.v[vi].census, cen_rt[1 - vi], w, h, lo[vi], hi[vi], gminv[vi], s.v[vi].C, st,
                              zoom == 2 ? cen_half[1 - vi] : nullptr, zoom);
         }
         if (rc != S2PB_OK) return rc;
@@ -1126,13 +1146,18 @@ static int mgm_enqueue(s2pb_ctx *ctx, Slot &s, const float *d_im1, const float *
             ctx->launches++;
             rc = cudaGetLastError() == cudaSuccess ? S2PB_OK : fail(S2PB_ERR_CUDA, "cost_chunked_kernel launch failed");
         } else {
-            rc = launch_cost(ctx, LPLv[vi], s.v[vi].census, s.v[1 - vi].census_rt, w, h, s.v[vi].lo, s.v[vi].hi, gminv[vi], s.v[vi].C, st);
+            rc = launch_cost(ctx, LPLv[vi], p->census_win, s.v[vi].census, s.v[1 - vi].census_rt, w, h, s.v[vi].lo, s.v[vi].hi, gminv[vi], s.v[vi].C, st);
         }
         if (rc != S2PB_OK) return rc;
     }
     CK(cudaEventRecord(s.ev[2], st));
     // ---- 8-pass MGM of both views in one persistent launch (two when the views' slabs differ in width)
-    if (LPLv[0] == LPLv[1]) rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, wide[0] ? gminv : nullptr);
+    // With another tile's aggregation queued or running (tiles in flight) the launch takes one CTA per SM instead of two, so two
+    // tiles' aggregations share the SMs: a pass is a chain of bands, 296 CTAs on 16 pass-views run it 18 bands deep and about a
+    // fifth of the launch is the chain filling and draining (measured by ignoring the hand-off: 3.39 -> 2.53 ms); two launches of
+    // 148 CTAs run 9 deep.  A/B on B200, C2 with 8 tiles in flight: 226.5 -> 236.9 Mpix/s (alone: 3.39 ms with 296, 3.96 with 148).
+    if (LPLv[0] == LPLv[1]) rc = launch_aggregate(ctx, s, 2, w, h, LPL, p->P1, p->P2, p->ndir, p->tsgm, lut, st, general, wgt, wide[0] ? gminv : nullptr,
+                                                  0, other_aggregation_pending(ctx, s) ? 1 : 0);
     else {
         // one launch per view, side by side: each takes one persistent CTA per SM (a chain of bands per pass limits what a single
         // view can keep busy: alone, 8 passes fill the GPU no better than 16 do), the right view on the slot's second stream
@@ -1511,7 +1536,7 @@ extern "C" int s2pb_costvolume(s2pb_ctx *ctx, const float *u, const float *v, in
     census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(du.as<float>(), w, h, win / 2, cu.as<uint64_t>());
     census_kernel<<<grid2d(w, h, b2), b2, 0, st>>>(dv.as<float>(), w, h, win / 2, cv.as<uint64_t>());
     ctx->launches += 2;
-    rc = launch_cost(ctx, LPL, cu.as<uint64_t>(), cv.as<uint64_t>(), w, h, dlo.as<short>(), dhi.as<short>(), gmin, dC.as<__half>(), st);
+    rc = launch_cost(ctx, LPL, win, cu.as<uint64_t>(), cv.as<uint64_t>(), w, h, dlo.as<short>(), dhi.as<short>(), gmin, dC.as<__half>(), st);
     if (rc != S2PB_OK) return rc;
     float lut_h[64];
     const float *lut = nullptr;
