@@ -120,6 +120,102 @@ __global__ void cost_kernel(const uint64_t *__restrict__ cu, const uint64_t *__r
     }
 }
 
+// The same volume for 32-bit census codes (3x3 / 5x5 windows) at full-pixel labels, one warp per strip of 32 consecutive pixels
+// of a row.  cost_kernel reads every code through its own 8-byte load at a lane stride of 8*LPL bytes: LPL loads of 8 L1
+// wavefronts each per pixel, and that -- not POPC, not issue -- is its bound (0.225 ms per C2 view whatever the arithmetic).  Here
+// the strip's 32 + DP matched-image codes are staged once in shared memory, in four copies shifted by 0..3 words, so that pixel i
+// reads its lane's LPL consecutive codes from copy i & 3 with aligned 16- / 8-byte loads (4 wavefronts for 512 bytes); the
+// pixel's own code and range come from registers of lane i by shuffle.  The range test is against warp-uniform bounds clamped
+// to the image, which also answers "does any label of the range have a distance" without a vote.  Same values as cost_kernel.
+constexpr int kCostStripThreads = 128;
+template <int LPL>
+__global__ void __launch_bounds__(kCostStripThreads) cost_strip_kernel(const uint64_t *__restrict__ cu, const uint64_t *__restrict__ cv, int w, int h,
+                                                                       const short *__restrict__ lo, const short *__restrict__ hi, int gmin,
+                                                                       __half *__restrict__ C)
+{
+    constexpr int DP = 32 * LPL, T = 32, NW = T + DP, CS = NW + 4;
+    __shared__ __align__(16) unsigned codes[kCostStripThreads / 32][4][CS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int spr = (w + T - 1) / T, total = h * spr;
+    const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * blockDim.x) >> 5);
+    unsigned (*mine)[CS] = codes[wib];
+    for (int strip = gw; strip < total; strip += nw) {
+        const int y = strip / spr, x0 = (strip - y * spr) * T;
+        const size_t row = (size_t)y * w;
+        __syncwarp();                                         // the previous strip's reads are done
+        for (int j = lane; j < NW; j += 32) {
+            const int q = x0 + gmin + j;
+            const unsigned c = (q >= 0 && q < w) ? reinterpret_cast<const unsigned *>(cv)[2 * (row + q)] : 0u;
+#pragma unroll
+            for (int sft = 0; sft < 4; sft++)
+                if (j - sft >= 0) mine[sft][j - sft] = c;     // copy sft: word k = code k + sft
+        }
+        const int xi = x0 + lane;
+        unsigned a_i = 0;
+        int l_i = 0, h_i = -1;
+        if (xi < w) { a_i = reinterpret_cast<const unsigned *>(cu)[2 * (row + xi)]; l_i = lo[row + xi]; h_i = hi[row + xi]; }
+        __syncwarp();
+        const int npx = (w - x0 < T) ? w - x0 : T;
+        __half *dst = C + (row + x0) * DP + lane * LPL;
+        for (int i = 0; i < npx; i++, dst += DP) {
+            const unsigned a = __shfl_sync(0xffffffffu, a_i, i);
+            const int l = __shfl_sync(0xffffffffu, l_i, i), hgh = __shfl_sync(0xffffffffu, h_i, i);
+            const int x = x0 + i;
+            int flo = l > -x ? l : -x, fhi = hgh < w - 1 - x ? hgh : w - 1 - x;       // labels of the range whose column is in the image
+            const bool none = flo > fhi;                       // no such label: the whole range is 0 (mgm_costvolume.cc:166-171)
+            if (none) { flo = l; fhi = hgh; }
+            const unsigned *src = &mine[i & 3][(i & ~3) + lane * LPL];
+            unsigned cw[LPL];
+            if constexpr (LPL % 4 == 0) {
+#pragma unroll
+                for (int q = 0; q < LPL / 4; q++) {
+                    const uint4 t = reinterpret_cast<const uint4 *>(src)[q];
+                    cw[4 * q] = t.x; cw[4 * q + 1] = t.y; cw[4 * q + 2] = t.z; cw[4 * q + 3] = t.w;
+                }
+            } else if constexpr (LPL % 2 == 0) {
+#pragma unroll
+                for (int q = 0; q < LPL / 2; q++) {
+                    const uint2 t = reinterpret_cast<const uint2 *>(src)[q];
+                    cw[2 * q] = t.x; cw[2 * q + 1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < LPL; e++) cw[e] = src[e];
+            }
+            unsigned cnt[LPL], fin = 0;
+#pragma unroll
+            for (int e = 0; e < LPL; e++) {
+                const int o = gmin + lane * LPL + e;
+                cnt[e] = none ? 0u : (unsigned)__popc(a ^ cw[e]);
+                if (o >= flo && o <= fhi) fin |= 1u << e;
+            }
+            if constexpr (LPL % 2 == 0) {
+                unsigned wds[LPL / 2];
+#pragma unroll
+                for (int e = 0; e < LPL / 2; e++) {
+                    unsigned pk = 0x64006400u + (cnt[2 * e] | (cnt[2 * e + 1] << 16));
+                    __half2 hv = __hsub2(*reinterpret_cast<__half2 *>(&pk), __half2half2(__ushort_as_half((unsigned short)0x6400)));
+                    const unsigned m = ((fin >> (2 * e)) & 1u ? 0x0000ffffu : 0u) | ((fin >> (2 * e + 1)) & 1u ? 0xffff0000u : 0u);
+                    wds[e] = (*reinterpret_cast<unsigned *>(&hv) & m) | (0x7c007c00u & ~m);
+                }
+                if constexpr (LPL % 8 == 0) {
+#pragma unroll
+                    for (int q = 0; q < LPL / 8; q++) reinterpret_cast<uint4 *>(dst)[q] = make_uint4(wds[4 * q], wds[4 * q + 1], wds[4 * q + 2], wds[4 * q + 3]);
+                } else if constexpr (LPL % 4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < LPL / 4; q++) reinterpret_cast<uint2 *>(dst)[q] = make_uint2(wds[2 * q], wds[2 * q + 1]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < LPL / 2; q++) reinterpret_cast<unsigned *>(dst)[q] = wds[q];
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < LPL; e++) dst[e] = (fin >> e) & 1u ? __float2half_rn((float)cnt[e]) : __ushort_as_half((unsigned short)0x7c00);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ general cost volume (float32)
 
 // The other distances of the reference's table (mgm_costvolume.h:25-57,96-180) on one channel, plus census through

@@ -544,9 +544,14 @@ static int launch_aggregate(s2pb_ctx *ctx, Slot &s, int nviews, int w, int h, in
     return S2PB_OK;
 }
 
+// S2PB_COST_STRIP=0: the per-pixel cost kernel for every shape (A/B)
+static bool cost_strip_enabled() { static int v = -1; if (v < 0) { const char *e = getenv("S2PB_COST_STRIP"); v = e ? atoi(e) : 1; } return v != 0; }
 template <int LPL> static void launch_cost_t(const uint64_t *cu, const uint64_t *cv, const uint64_t *cv1, int zoom, bool narrow, int w, int h,
                                              const short *lo, const short *hi, int gmin, __half *C, int sm, cudaStream_t st)
 {
+    if constexpr (LPL <= 8) {
+        if (zoom != 2 && narrow && cost_strip_enabled()) { cost_strip_kernel<LPL><<<sm * 16, kCostStripThreads, 0, st>>>(cu, cv, w, h, lo, hi, gmin, C); return; }
+    }
     if (zoom == 2) {
         if (narrow) cost_kernel<LPL, true, true><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
         else cost_kernel<LPL, true, false><<<sm * 8, 256, 0, st>>>(cu, cv, cv1, w, h, lo, hi, gmin, C);
