@@ -65,26 +65,45 @@ __global__ void rt_flag_kernel(const float *__restrict__ img, int w, int h, floa
 
 // Y[r][o] = (sum_{i=0}^{n-1} T[o][i] * X[r][i]) * scale-by-division, r over the listed rows (or all rows when
 // rowlist == nullptr).  The sum runs in ascending i with separately rounded multiply and add, from 0.0, like a plain C
-// loop compiled without contraction.  T is [n][n] row-major.  64 outputs x 32 rows per block, 4 x 2 per thread (the FP64
-// pipe issues one warp instruction every two cycles, so a small register tile already keeps it busy; the smaller tile
-// gives 512 work items on a 1024 x 1024 image for the 148 SMs).
+// loop compiled without contraction.  T is [n][n] row-major.  64 outputs x 32 rows per block of 128 threads, 4 x 4 per
+// thread: a thread's four T values and four X values of one i are two 16-byte shared loads each, i.e. four loads per
+// sixteen multiply-add pairs (the first version's 4 x 2 tile with 8-byte loads needed six per eight and was bound by them:
+// 41 % of the FP64 rate, profiles/r02_ncu_dct_kernels.txt).  512 work items on a 1024 x 1024 image for the 148 SMs.
 // IN = float (image rows) or double.  DIVN: divide the sum by n (the forward transform's normalisation, shear.c:62-63).
 // `mul` (optional, [n]): the output is multiplied by mul[o] (the phase factor cos(o a));
 // `mul2`/`Y2` (optional): a second output Y2[r][o-1] = y * mul2[o] for o >= 1 and Y2[r][n-1] = 0 (the antisymmetric
 // part's input, shear.c:71-79).
-template <typename IN, bool DIVN>
-__global__ void __launch_bounds__(256) dct_gemm_kernel(const double *__restrict__ T, const IN *__restrict__ X, int n, int nrows_all,
-                                                       const RtState *st, const int *__restrict__ rowlist,
-                                                       double *__restrict__ Y, const double *__restrict__ mul,
-                                                       const double *__restrict__ mul2, double *__restrict__ Y2)
+constexpr int kGemmThreads = 128, kGemmTO = 64, kGemmTR = 32, kGemmTK = 16;
+// one tile product: acc[qa][qb] += Ts[kk][gemm_out(tx, qa)] * Xs[kk][4 ty + qb] for kk < kmax, in ascending kk.  A thread's four
+// outputs are two adjacent pairs 32 apart (2 tx, 2 tx + 1, 32 + 2 tx, 33 + 2 tx): the lanes' 16-byte loads are then contiguous
+// (a 4-consecutive mapping strides them by 32 bytes: two wavefronts per load).
+__device__ __forceinline__ int gemm_out(int tx, int qa) { return (qa < 2) ? 2 * tx + qa : 32 + 2 * tx + (qa - 2); }
+__device__ __forceinline__ void gemm_tile_fp64(const double (*Ts)[kGemmTO + 2], const double (*Xs)[kGemmTR + 2], int kmax, int tx, int ty,
+                                               double (&acc)[4][4])
 {
-    constexpr int TO = 64, TR = 32, TK = 16, QA = 4, QB = 2;
-    __shared__ double Ts[TK][TO + 2];
-    __shared__ double Xs[TK][TR + 2];
+    for (int kk = 0; kk < kmax; kk++) {
+        const double2 a01 = *reinterpret_cast<const double2 *>(&Ts[kk][2 * tx]), a23 = *reinterpret_cast<const double2 *>(&Ts[kk][32 + 2 * tx]);
+        const double2 b01 = *reinterpret_cast<const double2 *>(&Xs[kk][4 * ty]), b23 = *reinterpret_cast<const double2 *>(&Xs[kk][4 * ty + 2]);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int qa = 0; qa < 4; qa++)
+#pragma unroll
+            for (int qb = 0; qb < 4; qb++) acc[qa][qb] = __dadd_rn(acc[qa][qb], __dmul_rn(a[qa], b[qb]));
+    }
+}
+template <typename IN, bool DIVN>
+__global__ void __launch_bounds__(kGemmThreads) dct_gemm_kernel(const double *__restrict__ T, const IN *__restrict__ X, int n, int nrows_all,
+                                                                const RtState *st, const int *__restrict__ rowlist,
+                                                                double *__restrict__ Y, const double *__restrict__ mul,
+                                                                const double *__restrict__ mul2, double *__restrict__ Y2)
+{
+    constexpr int TO = kGemmTO, TR = kGemmTR, TK = kGemmTK;
+    __shared__ __align__(16) double Ts[TK][TO + 2];
+    __shared__ __align__(16) double Xs[TK][TR + 2];
     __shared__ int rows_s[TR];
     const int nrows = rowlist ? st->nrows : nrows_all;
     const int otiles = (n + TO - 1) / TO, rtiles = (nrows + TR - 1) / TR;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;         // outputs gemm_out(tx, 0..3), rows 4 ty .. +3
     for (int item = blockIdx.x; item < otiles * rtiles; item += gridDim.x) {
         const int o0 = (item % otiles) * TO, r0 = (item / otiles) * TR;
         __syncthreads();
@@ -92,49 +111,42 @@ __global__ void __launch_bounds__(256) dct_gemm_kernel(const double *__restrict_
             const int rr = r0 + threadIdx.x;
             rows_s[threadIdx.x] = rr < nrows ? (rowlist ? rowlist[rr] : rr) : -1;
         }
-        double acc[QA][QB];
+        double acc[4][4];
 #pragma unroll
-        for (int a = 0; a < QA; a++)
+        for (int qa = 0; qa < 4; qa++)
 #pragma unroll
-            for (int b = 0; b < QB; b++) acc[a][b] = 0.0;
+            for (int qb = 0; qb < 4; qb++) acc[qa][qb] = 0.0;
+        // T tile: 64 outputs x 16 inputs, thread t holds output (t >> 1), inputs 8 (t & 1) .. +7; X tile: 32 rows x 16 inputs, thread t
+        // holds row (t >> 2), inputs 4 (t & 3) .. +3.  The next tile's values are fetched into registers before the current tile's
+        // product, so the global-load latency hides behind 16 x 32 FP64 instructions instead of standing between two barriers.
+        __syncthreads();                                             // rows_s is visible
+        const int to = o0 + (threadIdx.x >> 1), tkk = 8 * (threadIdx.x & 1);
+        const int xrow = rows_s[threadIdx.x >> 2], xkk = 4 * (threadIdx.x & 3);
+        double tv[8], xv[4];
+        auto fetch = [&](int k0) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int k = k0 + tkk + q; tv[q] = (to < n && k < n) ? T[(size_t)to * n + k] : 0.0; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const int k = k0 + xkk + q; xv[q] = (xrow >= 0 && k < n) ? (double)X[(size_t)xrow * n + k] : 0.0; }
+        };
+        fetch(0);
         for (int k0 = 0; k0 < n; k0 += TK) {
+            __syncthreads();                                         // the previous product is done with the tiles
+#pragma unroll
+            for (int q = 0; q < 8; q++) Ts[tkk + q][threadIdx.x >> 1] = tv[q];
+#pragma unroll
+            for (int q = 0; q < 4; q++) Xs[xkk + q][threadIdx.x >> 2] = xv[q];
             __syncthreads();
-            {   // T tile: 64 outputs x 16 inputs; thread t loads output (t >> 2), inputs 4 (t & 3) .. +3
-                const int o = o0 + (threadIdx.x >> 2), kk = 4 * (threadIdx.x & 3);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int k = k0 + kk + q;
-                    Ts[kk + q][threadIdx.x >> 2] = (o < n && k < n) ? T[(size_t)o * n + k] : 0.0;
-                }
-                // X tile: 32 rows x 16 inputs; thread t loads row (t >> 3), inputs 2 (t & 7), + 1
-                const int row = rows_s[threadIdx.x >> 3], kx = 2 * (threadIdx.x & 7);
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int k = k0 + kx + q;
-                    Xs[kx + q][threadIdx.x >> 3] = (row >= 0 && k < n) ? (double)X[(size_t)row * n + k] : 0.0;
-                }
-            }
-            __syncthreads();
-            const int kmax = (n - k0 < TK) ? n - k0 : TK;
-            for (int kk = 0; kk < kmax; kk++) {
-                double a[QA], b[QB];
-#pragma unroll
-                for (int q = 0; q < QA; q++) a[q] = Ts[kk][tx + 16 * q];
-#pragma unroll
-                for (int q = 0; q < QB; q++) b[q] = Xs[kk][ty + 16 * q];
-#pragma unroll
-                for (int qa = 0; qa < QA; qa++)
-#pragma unroll
-                    for (int qb = 0; qb < QB; qb++) acc[qa][qb] = __dadd_rn(acc[qa][qb], __dmul_rn(a[qa], b[qb]));
-            }
+            if (k0 + TK < n) fetch(k0 + TK);
+            gemm_tile_fp64(Ts, Xs, (n - k0 < TK) ? n - k0 : TK, tx, ty, acc);
         }
 #pragma unroll
-        for (int qb = 0; qb < QB; qb++) {
-            const int row = rows_s[ty + 16 * qb];
+        for (int qb = 0; qb < 4; qb++) {
+            const int row = rows_s[4 * ty + qb];
             if (row < 0) continue;
 #pragma unroll
-            for (int qa = 0; qa < QA; qa++) {
-                const int o = o0 + tx + 16 * qa;
+            for (int qa = 0; qa < 4; qa++) {
+                const int o = o0 + gemm_out(tx, qa);
                 if (o >= n) continue;
                 double y = acc[qa][qb];
                 if (DIVN) y = __ddiv_rn(y, (double)n);
@@ -165,13 +177,13 @@ __global__ void rt_collist_kernel(const unsigned char *__restrict__ colflag, int
 // the listed rows x the listed columns only -- a no-data margin is a few percent of the columns, so the inverse costs a few
 // percent of the forward transform; with a ragged mask the column list grows towards the full width and the cost towards
 // that of the forward one.  T01 is [n][n] row-major (output pixel, coefficient).
-__global__ void __launch_bounds__(256) rt_inverse_gemm_kernel(const double *__restrict__ T01, const double *__restrict__ Y, int n,
-                                                              const RtState *st, const int *__restrict__ rowlist, const int *__restrict__ collist,
-                                                              const float *__restrict__ rowthr, const float *__restrict__ img, float *__restrict__ rt)
+__global__ void __launch_bounds__(kGemmThreads) rt_inverse_gemm_kernel(const double *__restrict__ T01, const double *__restrict__ Y, int n,
+                                                                       const RtState *st, const int *__restrict__ rowlist, const int *__restrict__ collist,
+                                                                       const float *__restrict__ rowthr, const float *__restrict__ img, float *__restrict__ rt)
 {
-    constexpr int TO = 64, TR = 32, TK = 16, QA = 4, QB = 2;
-    __shared__ double Ts[TK][TO + 2];
-    __shared__ double Xs[TK][TR + 2];
+    constexpr int TO = kGemmTO, TR = kGemmTR, TK = kGemmTK;
+    __shared__ __align__(16) double Ts[TK][TO + 2];
+    __shared__ __align__(16) double Xs[TK][TR + 2];
     __shared__ int rows_s[TR], cols_s[TO];
     const int nrows = st->nrows, ncols = st->ncols;
     const int otiles = (ncols + TO - 1) / TO, rtiles = (nrows + TR - 1) / TR;
@@ -181,49 +193,40 @@ __global__ void __launch_bounds__(256) rt_inverse_gemm_kernel(const double *__re
         __syncthreads();
         if (threadIdx.x < TR) rows_s[threadIdx.x] = (r0 + (int)threadIdx.x < nrows) ? rowlist[r0 + threadIdx.x] : -1;
         else if (threadIdx.x < TR + TO) { const int q = threadIdx.x - TR; cols_s[q] = (o0 + q < ncols) ? collist[o0 + q] : -1; }
-        double acc[QA][QB];
+        double acc[4][4];
 #pragma unroll
-        for (int a = 0; a < QA; a++)
+        for (int qa = 0; qa < 4; qa++)
 #pragma unroll
-            for (int b = 0; b < QB; b++) acc[a][b] = 0.0;
+            for (int qb = 0; qb < 4; qb++) acc[qa][qb] = 0.0;
+        __syncthreads();                                             // rows_s, cols_s are visible
+        const int tcol = cols_s[threadIdx.x >> 1], tkk = 8 * (threadIdx.x & 1);
+        const int xrow = rows_s[threadIdx.x >> 2], xkk = 4 * (threadIdx.x & 3);
+        double tv[8], xv[4];
+        auto fetch = [&](int k0) {                                   // (register prefetch of the next tiles, as in dct_gemm_kernel)
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int k = k0 + tkk + q; tv[q] = (tcol >= 0 && k < n) ? T01[(size_t)tcol * n + k] : 0.0; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const int k = k0 + xkk + q; xv[q] = (xrow >= 0 && k < n) ? Y[(size_t)xrow * n + k] : 0.0; }
+        };
+        fetch(0);
         for (int k0 = 0; k0 < n; k0 += TK) {
             __syncthreads();
-            {
-                const int col = cols_s[threadIdx.x >> 2], kk = 4 * (threadIdx.x & 3);
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int k = k0 + kk + q;
-                    Ts[kk + q][threadIdx.x >> 2] = (col >= 0 && k < n) ? T01[(size_t)col * n + k] : 0.0;
-                }
-                const int row = rows_s[threadIdx.x >> 3], kx = 2 * (threadIdx.x & 7);
+            for (int q = 0; q < 8; q++) Ts[tkk + q][threadIdx.x >> 1] = tv[q];
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int k = k0 + kx + q;
-                    Xs[kx + q][threadIdx.x >> 3] = (row >= 0 && k < n) ? Y[(size_t)row * n + k] : 0.0;
-                }
-            }
+            for (int q = 0; q < 4; q++) Xs[xkk + q][threadIdx.x >> 2] = xv[q];
             __syncthreads();
-            const int kmax = (n - k0 < TK) ? n - k0 : TK;
-            for (int kk = 0; kk < kmax; kk++) {
-                double a[QA], b[QB];
-#pragma unroll
-                for (int q = 0; q < QA; q++) a[q] = Ts[kk][tx + 16 * q];
-#pragma unroll
-                for (int q = 0; q < QB; q++) b[q] = Xs[kk][ty + 16 * q];
-#pragma unroll
-                for (int qa = 0; qa < QA; qa++)
-#pragma unroll
-                    for (int qb = 0; qb < QB; qb++) acc[qa][qb] = __dadd_rn(acc[qa][qb], __dmul_rn(a[qa], b[qb]));
-            }
+            if (k0 + TK < n) fetch(k0 + TK);
+            gemm_tile_fp64(Ts, Xs, (n - k0 < TK) ? n - k0 : TK, tx, ty, acc);
         }
 #pragma unroll
-        for (int qb = 0; qb < QB; qb++) {
-            const int row = rows_s[ty + 16 * qb];
+        for (int qb = 0; qb < 4; qb++) {
+            const int row = rows_s[4 * ty + qb];
             if (row < 0) continue;
             const float thr = rowthr[row];
 #pragma unroll
-            for (int qa = 0; qa < QA; qa++) {
-                const int col = cols_s[tx + 16 * qa];
+            for (int qa = 0; qa < 4; qa++) {
+                const int col = cols_s[gemm_out(tx, qa)];
                 if (col < 0) continue;
                 const size_t p = (size_t)row * n + col;
                 if (fabsf(img[p]) <= thr) rt[p] = (float)__dmul_rn(0.5, __dadd_rn(acc[qa][qb], 0.0));

@@ -692,8 +692,8 @@ static int round_trip_zero(s2pb_ctx *ctx, const float *img, int w, int h, float 
     CK(cudaMemsetAsync(colflag, 0, (size_t)w, st));
     rt_flag_kernel<<<h, 256, 0, st>>>(img, w, h, rt, state, rowlist, rowthr, colflag);
     rt_collist_kernel<<<1, 1024, 0, st>>>(colflag, w, state, collist);
-    dct_gemm_kernel<float, true><<<ctx->sm_count * 4, 256, 0, st>>>(t->T10, img, w, h, state, rowlist, Y, nullptr, nullptr, nullptr);
-    rt_inverse_gemm_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(t->T01, Y, w, state, rowlist, collist, rowthr, img, rt);
+    dct_gemm_kernel<float, true><<<ctx->sm_count * 4, kGemmThreads, 0, st>>>(t->T10, img, w, h, state, rowlist, Y, nullptr, nullptr, nullptr);
+    rt_inverse_gemm_kernel<<<ctx->sm_count * 4, kGemmThreads, 0, st>>>(t->T01, Y, w, state, rowlist, collist, rowthr, img, rt);
     ctx->launches += 4;
     CK(cudaGetLastError());
     return S2PB_OK;
@@ -708,9 +708,9 @@ static int shift_half(s2pb_ctx *ctx, const float *img, int w, int h, float *out,
     const size_t npix = (size_t)w * h;
     double *ck = scratch, *sk = scratch + npix, *sym = scratch + 2 * npix, *anti = scratch + 3 * npix;
     const int g = ctx->sm_count * 4;
-    dct_gemm_kernel<float, true><<<g, 256, 0, st>>>(t->T10, img, w, h, nullptr, nullptr, ck, t->mc, t->ms, sk);
-    dct_gemm_kernel<double, false><<<g, 256, 0, st>>>(t->T01, ck, w, h, nullptr, nullptr, sym, nullptr, nullptr, nullptr);
-    dct_gemm_kernel<double, false><<<g, 256, 0, st>>>(t->TR01, sk, w, h, nullptr, nullptr, anti, nullptr, nullptr, nullptr);
+    dct_gemm_kernel<float, true><<<g, kGemmThreads, 0, st>>>(t->T10, img, w, h, nullptr, nullptr, ck, t->mc, t->ms, sk);
+    dct_gemm_kernel<double, false><<<g, kGemmThreads, 0, st>>>(t->T01, ck, w, h, nullptr, nullptr, sym, nullptr, nullptr, nullptr);
+    dct_gemm_kernel<double, false><<<g, kGemmThreads, 0, st>>>(t->TR01, sk, w, h, nullptr, nullptr, anti, nullptr, nullptr, nullptr);
     dct_combine_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(sym, anti, npix, out);
     ctx->launches += 4;
     CK(cudaGetLastError());
