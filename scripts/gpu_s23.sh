@@ -1,7 +1,7 @@
 #!/bin/bash
 # session 23: evidence after the WTA series -- suite, every kernel in one ncu pass, full captures of the aggregation and the WTA,
 # launch list of one C2 tile, the default bench line and the reference arm
-O=gpurun_out/r02s23; mkdir -p $O
+O=gpurun_out/r02s35; mkdir -p $O
 export PARITY=0
 timeout 900 python -m pytest tests -m gpu -q --timeout 180 2>&1 | tail -6 > $O/tests.log; tail -2 $O/tests.log
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size \
@@ -18,9 +18,9 @@ timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench_n1.json 2> $O/bench
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_n1.json 2> $O/bench_ref.err
 python - <<'P'
 import json
-d = json.load(open("gpurun_out/r02s23/bench_n1.json"))
+d = json.load(open("gpurun_out/r02s35/bench_n1.json"))
 print("value %.1f e2e %.1f agg %.3f verified %s cpu %s launches %s" % (d["value"], d["e2e"]["value"], d["roofline"]["kernel_ms"], d.get("outputs_verified"), d["cpu_baseline"]["value"], d["gpu_launches"]))
 for k, v in d.get("extra_configs", {}).items():
     print(k, {x: (round(v[x], 2) if isinstance(v[x], float) else v[x]) for x in ("value", "error", "ms_per_tile", "seconds", "ms_per_warp") if x in v}, "e2e", round(v["e2e"]["value"], 1), "cpu", (v.get("cpu_baseline") or {}).get("value"))
-r = json.load(open("gpurun_out/r02s23/bench_reference_n1.json")); print("reference", r.get("value"), r.get("cpu_baseline", {}).get("sample", "")[:120])
+r = json.load(open("gpurun_out/r02s35/bench_reference_n1.json")); print("reference", r.get("value"), r.get("cpu_baseline", {}).get("sample", "")[:120])
 P
