@@ -128,7 +128,10 @@ int s2pb_mgm_device(s2pb_ctx *ctx, int slot, const float *d_im1, const float *d_
 
 /* n independent tiles of identical shape, pipelined over the context's slots
  * (staging or direct DMA as above, H2D / compute / D2H of different tiles overlap).
- * Arrays of n host pointers. */
+ * Arrays of n host pointers.  For the multi-scale algorithms (scales >= 0), which read a
+ * label hull back at every pyramid level, the tiles are driven by one host thread per
+ * workspace inside the call (at most four); a context may also be used from several
+ * caller threads as long as each uses its own slot. */
 int s2pb_mgm_batch(s2pb_ctx *ctx, int n, const float *const *im1, const float *const *im2,
                    int w, int h, int dmin, int dmax, const s2pb_mgm_params *p,
                    float *const *disp, float *const *conf, uint8_t *const *mask);
